@@ -1,0 +1,479 @@
+// dv_capi.cu -- the C ABI of libdivans_b200.so: batch engine context + the reference's FFI surface as a drop-in.
+//
+// Host side only marshals: offsets/lengths tables, H2D/D2H copies, kernel launches.  All model/entropy work runs in
+// the sm_100a kernels (dv_kernels.cu); there is no CPU decode path in this library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/divans_b200.h"
+#include "dv_kernels.h"
+
+#ifndef DV_TABLES_PATH
+#error "DV_TABLES_PATH must point at brotli_tables.bin"
+#endif
+__asm__(".section .rodata\n"
+        ".global dv_tables_blob\n"
+        ".balign 16\n"
+        "dv_tables_blob:\n"
+        ".incbin \"" DV_TABLES_PATH "\"\n"
+        ".previous\n");
+extern "C" const uint8_t dv_tables_blob[];
+
+using namespace dv;
+
+struct divans_b200_ctx {
+    int device = 0;
+    int lanes_per_stream = 32;
+    int sm_count = 0;
+    uint32_t max_resident = 0;       // slots in the arena
+    cudaStream_t stream = nullptr;
+    uint8_t *d_arena = nullptr; size_t arena_slots = 0;
+    uint8_t *d_tables = nullptr;
+    uint32_t *d_counter = nullptr;
+    uint64_t *d_nibbles = nullptr;
+    // grow-only scratch
+    uint32_t *d_body_end = nullptr; size_t body_end_cap = 0;
+    uint8_t *d_in = nullptr; size_t d_in_cap = 0;
+    uint8_t *d_out = nullptr; size_t d_out_cap = 0;
+    uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;   // in_off,in_len,out_off,out_cap,out_len (+status)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;
+    uint64_t launches = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+static bool ck(divans_b200_ctx *c, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    char buf[512];
+    snprintf(buf, sizeof buf, "divans_b200: %s failed: %s", what, cudaGetErrorString(e));
+    if (c) c->err = buf;
+    fprintf(stderr, "%s\n", buf);
+    return false;
+}
+#define CK(call) do { if (!ck(ctx, (call), #call)) return DIVANS_FAILURE; } while (0)
+
+template <typename T>
+static bool grow(divans_b200_ctx *ctx, T **p, size_t *cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 4 + 256;
+    if (!ck(ctx, cudaMalloc((void **)p, want * sizeof(T)), "cudaMalloc(scratch)")) return false;
+    *cap = want;
+    return true;
+}
+
+extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream) {
+    divans_b200_ctx *ctx = new divans_b200_ctx();
+    ctx->device = device;
+    ctx->lanes_per_stream = lanes_per_stream == 16 ? 16 : 32;
+    cudaDeviceProp prop;
+    if (!ck(ctx, cudaSetDevice(device), "cudaSetDevice") || !ck(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
+        fprintf(stderr, "divans_b200: no usable CUDA device %d -- this library has no CPU path\n", device);
+        delete ctx; return nullptr;
+    }
+    if (prop.major < 10) {
+        fprintf(stderr, "divans_b200: device %d is sm_%d%d; the kernels are built for sm_100a only\n", device, prop.major, prop.minor);
+        delete ctx; return nullptr;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = ck(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              ck(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate") &&
+              ck(ctx, cudaMalloc((void **)&ctx->d_tables, TB_TOTAL), "cudaMalloc(tables)") &&
+              ck(ctx, cudaMemcpy(ctx->d_tables, dv_tables_blob, TB_TOTAL, cudaMemcpyHostToDevice), "cudaMemcpy(tables)") &&
+              ck(ctx, cudaMalloc((void **)&ctx->d_counter, 64), "cudaMalloc(counter)") &&
+              ck(ctx, cudaMalloc((void **)&ctx->d_nibbles, 64), "cudaMalloc(nibbles)") &&
+              ck(ctx, cudaMemset(ctx->d_nibbles, 0, 64), "cudaMemset") &&
+              ck(ctx, upload_ctx_lut32(dv_tables_blob + TB_CTX), "upload ctx lut") &&
+              ck(ctx, upload_ctx_lut16(dv_tables_blob + TB_CTX), "upload ctx lut");
+    if (!ok) { delete ctx; return nullptr; }
+    int per_sm = ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
+    if (per_sm < 1) per_sm = 1;
+    uint32_t groups_per_block = DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    uint32_t auto_res = (uint32_t)ctx->sm_count * (uint32_t)per_sm * groups_per_block;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    uint32_t mem_cap = (uint32_t)((free_b * 6 / 10) / SLOT_STRIDE);   // leave room for batch buffers
+    if (auto_res > mem_cap) auto_res = mem_cap;
+    ctx->max_resident = max_resident ? (max_resident < auto_res ? max_resident : auto_res) : auto_res;
+    if (ctx->max_resident < groups_per_block) ctx->max_resident = groups_per_block;
+    return ctx;
+}
+
+extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_arena); cudaFree(ctx->d_tables); cudaFree(ctx->d_counter); cudaFree(ctx->d_nibbles);
+    cudaFree(ctx->d_body_end); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char *divans_b200_last_error(divans_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t divans_b200_launch_count(divans_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" float divans_b200_last_kernel_ms(divans_b200_ctx *ctx) {
+    if (!ctx) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
+    return ctx->last_kernel_ms;
+}
+extern "C" DivansResult divans_b200_synchronize(divans_b200_ctx *ctx) {
+    if (!ctx) return DIVANS_FAILURE;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DIVANS_SUCCESS;
+}
+
+static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
+    if (slots <= ctx->arena_slots) return DIVANS_SUCCESS;
+    if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; ctx->arena_slots = 0; }
+    CK(cudaMalloc((void **)&ctx->d_arena, slots * SLOT_STRIDE));
+    ctx->arena_slots = slots;
+    return DIVANS_SUCCESS;
+}
+
+extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                                        const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
+                                                        const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
+                                                        uint32_t flags, void *cuda_stream) {
+    if (!ctx) return DIVANS_FAILURE;
+    if (n == 0) return DIVANS_SUCCESS;
+    if (n > 0xffffffffull) { ctx->err = "too many streams"; return DIVANS_FAILURE; }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    uint32_t gpb = DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    uint32_t resident = (uint32_t)(n < ctx->max_resident ? n : ctx->max_resident);
+    uint32_t blocks = (resident + gpb - 1) / gpb;
+    if (ensure_arena(ctx, (size_t)blocks * gpb) != DIVANS_SUCCESS) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_body_end, &ctx->body_end_cap, n)) return DIVANS_FAILURE;
+    CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
+    FrameParams fp;
+    fp.in = d_in; fp.in_off = d_in_off; fp.in_len = d_in_len; fp.body_end = ctx->d_body_end; fp.status = d_status;
+    fp.n_streams = (uint32_t)n; fp.flags = flags;
+    DecodeParams dp;
+    dp.in = d_in; dp.in_off = d_in_off; dp.in_len = d_in_len; dp.out = d_out; dp.out_off = d_out_off; dp.out_cap = d_out_cap;
+    dp.out_len = d_out_len; dp.status = d_status; dp.body_end = ctx->d_body_end; dp.n_streams = (uint32_t)n;
+    dp.work_counter = ctx->d_counter; dp.arena = ctx->d_arena; dp.tables = ctx->d_tables; dp.nibble_counts = ctx->d_nibbles;
+    static const bool dbg = getenv("DIVANS_B200_DEBUG") != nullptr;
+    static const bool skip_decode = getenv("DIVANS_B200_SKIP_DECODE") != nullptr;
+    CK(cudaEventRecord(ctx->ev0, st));
+    launch_frame(fp, st);
+    if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
+    if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
+    if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return DIVANS_SUCCESS;
+}
+
+extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                                      const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                                      const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags) {
+    if (!ctx) return DIVANS_FAILURE;
+    if (n == 0) return DIVANS_SUCCESS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    // extent of the input / output blobs
+    uint64_t in_end = 0, out_end = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
+        if (out_off[i] + out_cap[i] > out_end) out_end = out_off[i] + out_cap[i];
+    }
+    if (!grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)in_end + 64)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)out_end + 64)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_meta, &ctx->d_meta_cap, n * 6)) return DIVANS_FAILURE;
+    uint64_t *m = ctx->d_meta;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_in, in, in_end, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m, in_off, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + n, in_len, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + 2 * n, out_off, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m + 3 * n, out_cap, n * 8, cudaMemcpyHostToDevice, st));
+    int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
+    DivansResult r = divans_b200_decode_batch_device(ctx, n, ctx->d_in, m, m + n, ctx->d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
+                                                     flags, st);
+    if (r != DIVANS_SUCCESS) return r;
+    CK(cudaMemcpyAsync(out_len, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // copy back only what was produced (contiguous runs are merged into one transfer)
+    size_t i = 0;
+    while (i < n) {
+        uint64_t lo = out_off[i], hi = out_off[i] + out_len[i];
+        size_t j = i + 1;
+        while (j < n && out_off[j] >= lo && out_off[j] <= hi + 4096) { uint64_t e = out_off[j] + out_len[j]; if (e > hi) hi = e; j++; }
+        if (hi > lo) CK(cudaMemcpyAsync(out + lo, ctx->d_out + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+        i = j;
+    }
+    CK(cudaStreamSynchronize(st));
+    return DIVANS_SUCCESS;
+}
+
+extern "C" void divans_b200_encode_options_default(divans_b200_encode_options *o) {
+    memset(o, 0, sizeof *o);
+    o->window_size = 22; o->dynamic_context_mixing = 0; o->prior_depth = 0; o->use_context_map = 1; o->force_stride = 9;
+    o->literal_pred_mode = 0; o->literal_mixing_value = 4;
+}
+extern "C" DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size_t, const uint8_t *, const uint64_t *, const uint64_t *,
+                                                      uint8_t *, const uint64_t *, const uint64_t *, uint64_t *, int32_t *,
+                                                      const divans_b200_encode_options *) {
+    if (ctx) ctx->err = "GPU encoder not built yet";
+    fprintf(stderr, "divans_b200: GPU encoder not implemented in this build\n");
+    return DIVANS_FAILURE;
+}
+extern "C" DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t, const uint8_t *, const uint64_t *,
+                                                           const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, uint64_t *,
+                                                           int32_t *, const divans_b200_encode_options *) {
+    if (ctx) ctx->err = "GPU encoder not built yet";
+    fprintf(stderr, "divans_b200: GPU encoder not implemented in this build\n");
+    return DIVANS_FAILURE;
+}
+
+// =================================================================================================================
+// reference FFI surface (src/ffi/mod.rs).  Streaming contract on top of batch-of-one GPU calls.
+// =================================================================================================================
+static divans_b200_ctx *g_shared_ctx = nullptr;
+static std::mutex g_shared_mu;
+static divans_b200_ctx *shared_ctx() {
+    std::lock_guard<std::mutex> lk(g_shared_mu);
+    if (!g_shared_ctx) {
+        int dev = 0;
+        const char *e = getenv("DIVANS_B200_DEVICE");
+        if (e) dev = atoi(e);
+        g_shared_ctx = divans_b200_create(dev, 0, 32);
+    }
+    return g_shared_ctx;
+}
+
+struct HostAlloc {   // CAllocator or malloc (ffi/alloc_util.rs:70-99: memory is zero-initialised)
+    CAllocator a{nullptr, nullptr, nullptr};
+    void *alloc(size_t n) {
+        void *p = a.alloc_func ? a.alloc_func(a.opaque, n) : malloc(n);
+        if (p) memset(p, 0, n);
+        return p;
+    }
+    void free(void *p) { if (!p) return; if (a.free_func) a.free_func(a.opaque, p); else ::free(p); }
+};
+
+struct DivansDecompressorState {
+    HostAlloc al;
+    bool self_in_custom = false;
+    uint8_t skip_crc = 0;
+    std::vector<uint8_t> *inbuf = nullptr;    // buffered compressed stream
+    std::vector<uint8_t> *outbuf = nullptr;   // decoded stream waiting to be handed out
+    size_t out_cursor = 0;
+    // incremental framing scan (host): how far the record chain has been walked
+    size_t scan_pos = 16; bool saw_eof = false; size_t total_len = 0; bool decoded = false; bool failed = false;
+};
+
+static DivansDecompressorState *new_decomp(CAllocator a, uint8_t skip_crc) {
+    DivansDecompressorState *s;
+    if (a.alloc_func) {
+        void *mem = a.alloc_func(a.opaque, sizeof(DivansDecompressorState));
+        if (!mem) return nullptr;
+        s = new (mem) DivansDecompressorState();
+        s->self_in_custom = true;
+    } else s = new DivansDecompressorState();
+    s->al.a = a; s->skip_crc = skip_crc;
+    s->inbuf = new std::vector<uint8_t>(); s->outbuf = new std::vector<uint8_t>();
+    if (!shared_ctx()) { s->failed = true; }
+    return s;
+}
+extern "C" DivansDecompressorState *divans_new_decompressor(void) { return new_decomp(CAllocator{nullptr, nullptr, nullptr}, 0); }
+extern "C" DivansDecompressorState *divans_new_serial_decompressor(void) { return new_decomp(CAllocator{nullptr, nullptr, nullptr}, 0); }
+extern "C" DivansDecompressorState *divans_new_decompressor_with_custom_alloc(CAllocator alloc, uint8_t skip_crc, uint8_t /*multithread*/) {
+    return new_decomp(alloc, skip_crc);
+}
+extern "C" void divans_free_decompressor(DivansDecompressorState *s) {
+    if (!s) return;
+    delete s->inbuf; delete s->outbuf;
+    if (s->self_in_custom) { HostAlloc al = s->al; s->~DivansDecompressorState(); al.free(s); }
+    else delete s;
+}
+extern "C" uint8_t *divans_decompressor_malloc_u8(DivansDecompressorState *s, size_t n) { return (uint8_t *)s->al.alloc(n); }
+extern "C" void divans_decompressor_free_u8(DivansDecompressorState *s, uint8_t *p, size_t) { s->al.free(p); }
+extern "C" size_t *divans_decompressor_malloc_usize(DivansDecompressorState *s, size_t n) { return (size_t *)s->al.alloc(n * sizeof(size_t)); }
+extern "C" void divans_decompressor_free_usize(DivansDecompressorState *s, size_t *p, size_t) { s->al.free(p); }
+
+// walk record headers over what has been buffered so far; sets saw_eof/total_len once the EOF marker is visible
+static int scan_frames(DivansDecompressorState *s) {
+    const std::vector<uint8_t> &b = *s->inbuf;
+    if (b.size() < 16) return 0;
+    if (b[0] != 0xff || b[1] != 0xe5 || b[2] != 0x8c || b[3] != 0x9f) return -1;
+    if (b[5] < 10 || b[5] >= 25) return -1;
+    while (!s->saw_eof) {
+        size_t pos = s->scan_pos;
+        if (pos >= b.size()) return 0;
+        uint8_t h = b[pos];
+        if (h == 0xff) {
+            if (pos + 3 > b.size()) return 0;
+            if (b[pos + 1] != 0xfe || b[pos + 2] != 0xff) return -1;
+            s->saw_eof = true; s->total_len = pos + 3 + 8;
+            break;
+        }
+        size_t len, hdr;
+        if (h < 16) { if (pos + 3 > b.size()) return 0; len = ((size_t)b[pos + 1] | ((size_t)b[pos + 2] << 8)) + 1; hdr = 3; }
+        else { unsigned k = h >> 4; if (k > 3) return -1; len = (size_t)1024 << (k << 1); hdr = 1; }
+        s->scan_pos = pos + hdr + len;   // may point beyond what is buffered; resolved when more input arrives
+    }
+    return 1;
+}
+
+extern "C" DivansResult divans_decode(DivansDecompressorState *s, const uint8_t *input_buf_ptr, size_t input_size, size_t *input_offset,
+                                      uint8_t *output_buf_ptr, size_t output_size, size_t *output_offset) {
+    if (!s || !input_offset || !output_offset) return DIVANS_FAILURE;   // ffi/mod.rs:241-262
+    if (s->failed) return DIVANS_FAILURE;
+    if (!s->decoded) {
+        // take input until the whole stream (through the 8-byte trailer) is buffered
+        while (*input_offset < input_size) {
+            size_t want;
+            if (s->saw_eof) want = s->total_len - s->inbuf->size();
+            else {
+                size_t have = s->inbuf->size();
+                size_t target = have < 16 ? 16 : (s->scan_pos + 3 > have ? s->scan_pos + 3 : have + 1);
+                want = target - have;
+            }
+            if (want == 0) break;
+            size_t avail = input_size - *input_offset;
+            size_t take = want < avail ? want : avail;
+            s->inbuf->insert(s->inbuf->end(), input_buf_ptr + *input_offset, input_buf_ptr + *input_offset + take);
+            *input_offset += take;
+            int sc = scan_frames(s);
+            if (sc < 0) { s->failed = true; return DIVANS_FAILURE; }
+            if (s->saw_eof && s->inbuf->size() >= s->total_len) break;
+        }
+        if (!(s->saw_eof && s->inbuf->size() >= s->total_len)) return DIVANS_NEEDS_MORE_INPUT;
+        divans_b200_ctx *ctx = shared_ctx();
+        if (!ctx) { s->failed = true; return DIVANS_FAILURE; }
+        // output size is not in the header: start from a guess, double on NEEDS_MORE_OUTPUT
+        size_t cap = s->inbuf->size() * 8 + (1 << 16);
+        for (;;) {
+            s->outbuf->resize(cap);
+            uint64_t in_off = 0, in_len = s->inbuf->size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
+            DivansResult r = divans_b200_decode_batch_host(ctx, 1, s->inbuf->data(), &in_off, &in_len, s->outbuf->data(), &out_off, &out_cap,
+                                                           &out_len, &status, s->skip_crc ? DIVANS_B200_FLAG_SKIP_CRC : 0);
+            if (r != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
+            if (status == DIVANS_NEEDS_MORE_OUTPUT && cap < ((size_t)1 << 34)) { cap *= 4; continue; }
+            if (status != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
+            s->outbuf->resize(out_len);
+            break;
+        }
+        s->decoded = true;
+        std::vector<uint8_t>().swap(*s->inbuf);
+    }
+    size_t remaining = s->outbuf->size() - s->out_cursor;
+    size_t room = output_size - *output_offset;
+    size_t give = remaining < room ? remaining : room;
+    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf->data() + s->out_cursor, give);
+    s->out_cursor += give; *output_offset += give;
+    return s->out_cursor == s->outbuf->size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
+}
+
+// ---- compressor side ----
+struct DivansCompressorState {
+    HostAlloc al;
+    bool self_in_custom = false;
+    divans_b200_encode_options opts;
+    int use_brotli = 1;
+    bool started = false, flushed = false, failed = false;
+    std::vector<uint8_t> *inbuf = nullptr, *outbuf = nullptr;
+    size_t out_cursor = 0;
+};
+extern "C" DivansCompressorState *divans_new_compressor_with_custom_alloc(CAllocator a) {
+    DivansCompressorState *s;
+    if (a.alloc_func) {
+        void *mem = a.alloc_func(a.opaque, sizeof(DivansCompressorState));
+        if (!mem) return nullptr;
+        s = new (mem) DivansCompressorState(); s->self_in_custom = true;
+    } else s = new DivansCompressorState();
+    s->al.a = a;
+    divans_b200_encode_options_default(&s->opts);
+    s->opts.dynamic_context_mixing = 1;   // DivansCompressorOptions::default(), src/interface.rs:462-484
+    s->inbuf = new std::vector<uint8_t>(); s->outbuf = new std::vector<uint8_t>();
+    return s;
+}
+extern "C" DivansCompressorState *divans_new_compressor(void) { return divans_new_compressor_with_custom_alloc(CAllocator{nullptr, nullptr, nullptr}); }
+extern "C" void divans_free_compressor(DivansCompressorState *s) {
+    if (!s) return;
+    delete s->inbuf; delete s->outbuf;
+    if (s->self_in_custom) { HostAlloc al = s->al; s->~DivansCompressorState(); al.free(s); }
+    else delete s;
+}
+extern "C" uint8_t *divans_compressor_malloc_u8(DivansCompressorState *s, size_t n) { return (uint8_t *)s->al.alloc(n); }
+extern "C" void divans_compressor_free_u8(DivansCompressorState *s, uint8_t *p, size_t) { s->al.free(p); }
+extern "C" size_t *divans_compressor_malloc_usize(DivansCompressorState *s, size_t n) { return (size_t *)s->al.alloc(n * sizeof(size_t)); }
+extern "C" void divans_compressor_free_usize(DivansCompressorState *s, size_t *p, size_t) { s->al.free(p); }
+
+static const int16_t kPalette[15][2] = {   // Speed::ENCODER_DEFAULT_PALETTE, probability/interface.rs:303-320
+    {0, 1024}, {2, 1024}, {1, 128}, {1, 16384}, {2, 2048}, {4, 1024}, {8, 8192}, {16, 48}, {16, 8192}, {32, 4096},
+    {64, 16384}, {128, 256}, {128, 16384}, {512, 16384}, {1664, 16384}};
+extern "C" DivansResult divans_set_option(DivansCompressorState *s, DivansOptionSelect selector, uint32_t value) {
+    if (!s || s->started) return DIVANS_FAILURE;   // options only in the OptionStage, ffi/compressor.rs:63-166
+    divans_b200_encode_options &o = s->opts;
+    auto set_adapt = [&](int idx) -> DivansResult {
+        if (value >= 15) return DIVANS_FAILURE;
+        if (!o.have_literal_adaptation) { o.have_literal_adaptation = 1; for (int k = 0; k < 4; k++) { o.literal_adaptation[k][0] = kPalette[value][0]; o.literal_adaptation[k][1] = kPalette[value][1]; } }
+        else { o.literal_adaptation[idx][0] = kPalette[value][0]; o.literal_adaptation[idx][1] = kPalette[value][1]; }
+        return DIVANS_SUCCESS;
+    };
+    switch (selector) {
+    case DIVANS_OPTION_QUALITY: case DIVANS_OPTION_LGBLOCK: case DIVANS_OPTION_STRIDE_DETECTION_QUALITY:
+    case DIVANS_OPTION_PRIOR_BITMASK_DETECTION: case DIVANS_OPTION_SPEED_DETECTION_QUALITY: case DIVANS_OPTION_BROTLI_LITERAL_BYTE_SCORE:
+    case DIVANS_OPTION_Q9_5: case DIVANS_OPTION_IR_OPTIMIZER:
+        return DIVANS_SUCCESS;   // command-selection knobs of the brotli crate: accepted, no effect on the entropy half
+    case DIVANS_OPTION_WINDOW_SIZE: o.window_size = (int32_t)value; return DIVANS_SUCCESS;
+    case DIVANS_OPTION_DYNAMIC_CONTEXT_MIXING: o.dynamic_context_mixing = (int32_t)(value & 0xff); return DIVANS_SUCCESS;
+    case DIVANS_OPTION_USE_BROTLI_COMMAND_SELECTION: if (value > 2) return DIVANS_FAILURE; s->use_brotli = (int)value; return DIVANS_SUCCESS;
+    case DIVANS_OPTION_USE_BROTLI_BITSTREAM: if (value != 1) return DIVANS_FAILURE; s->use_brotli = 2; return DIVANS_SUCCESS;
+    case DIVANS_OPTION_USE_CONTEXT_MAP: if (value > 1) return DIVANS_FAILURE; o.use_context_map = (int32_t)value; return DIVANS_SUCCESS;
+    case DIVANS_OPTION_FORCE_STRIDE_VALUE: if (value > 8) return DIVANS_FAILURE; o.force_stride = (int32_t)value; return DIVANS_SUCCESS;
+    case DIVANS_OPTION_LITERAL_ADAPTATION_STRIDE_HIGH: return set_adapt(1);
+    case DIVANS_OPTION_LITERAL_ADAPTATION_CM_HIGH: return set_adapt(3);
+    case DIVANS_OPTION_LITERAL_ADAPTATION_STRIDE_LOW: return set_adapt(0);
+    case DIVANS_OPTION_LITERAL_ADAPTATION_CM_LOW: return set_adapt(2);
+    case DIVANS_OPTION_PRIOR_DEPTH: o.prior_depth = (int32_t)(value & 0xff); return DIVANS_SUCCESS;
+    case DIVANS_OPTION_FORCE_LITERAL_CONTEXT_MODE: o.literal_pred_mode = (int32_t)(value & 0xff); return DIVANS_SUCCESS;
+    default: return DIVANS_FAILURE;
+    }
+}
+extern "C" DivansResult divans_encode(DivansCompressorState *s, const uint8_t *input_buf_ptr, size_t input_size, size_t *input_offset,
+                                      uint8_t *, size_t, size_t *output_offset) {
+    if (!s || !input_offset || !output_offset) return DIVANS_FAILURE;
+    if (s->failed || s->flushed) return DIVANS_FAILURE;
+    s->started = true;
+    s->inbuf->insert(s->inbuf->end(), input_buf_ptr + *input_offset, input_buf_ptr + input_size);
+    *input_offset = input_size;
+    return DIVANS_NEEDS_MORE_INPUT;   // like the reference: all input consumed, nothing is "done" before flush
+}
+extern "C" DivansResult divans_encode_flush(DivansCompressorState *s, uint8_t *output_buf_ptr, size_t output_size, size_t *output_offset) {
+    if (!s || !output_offset) return DIVANS_FAILURE;
+    if (s->failed) return DIVANS_FAILURE;
+    s->started = true;
+    if (!s->flushed) {
+        divans_b200_ctx *ctx = shared_ctx();
+        if (!ctx) { s->failed = true; return DIVANS_FAILURE; }
+        size_t cap = s->inbuf->size() + s->inbuf->size() / 2 + 70000;
+        s->outbuf->resize(cap);
+        uint64_t in_off = 0, in_len = s->inbuf->size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
+        DivansResult r = divans_b200_encode_batch_host(ctx, 1, s->inbuf->data(), &in_off, &in_len, s->outbuf->data(), &out_off, &out_cap, &out_len,
+                                                       &status, &s->opts);
+        if (r != DIVANS_SUCCESS || status != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
+        s->outbuf->resize(out_len);
+        s->flushed = true;
+    }
+    size_t remaining = s->outbuf->size() - s->out_cursor, room = output_size - *output_offset;
+    size_t give = remaining < room ? remaining : room;
+    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf->data() + s->out_cursor, give);
+    s->out_cursor += give; *output_offset += give;
+    return s->out_cursor == s->outbuf->size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
+}

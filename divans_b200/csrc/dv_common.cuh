@@ -1,0 +1,99 @@
+// dv_common.cuh -- shared definitions for the sm_100a divANS kernels.
+//
+// Data layout in HBM (per resident "slot" = the private model state of one stream while a lane-group
+// decodes/encodes it; slots are recycled from stream to stream):
+//
+//   [LIT_HI  3*256*256 CDFs][LIT_LO 3*256*256 CDFs][LIT_CM 4352 CDFs][CTYPE 256 slabs x 32 CDFs]
+//   [DPRIOR 256 slabs x 32 CDFs][MISC 128 CDFs][literal ctx map 16384 B][mixing mask 8192 B][distance ctx map 1024 B]
+//
+// A CDF is 16 x int16 = 32 B = one DRAM sector; lane i of a 16-lane group owns element i.
+// The in-memory order of priors is NOT on the wire (reference: src/priors.rs:211-237 only fixes the index rule),
+// so the literal tables are laid out [which][index_c][index_b]: one (which, index_c) "slab" is 256 consecutive
+// CDFs (8 KiB) and is default-initialised lazily by the kernel the first time the stream's context map / mixing
+// mask makes it reachable -- no 12.6 MB memset per stream (the reference default-initialises all of it,
+// codec/interface.rs:728-729).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dv {
+
+constexpr uint32_t CDF_BYTES = 32;
+constexpr uint64_t LIT_TABLE_CDFS = 3ull * 256 * 256;
+constexpr uint64_t OFF_LIT_HI = 0;
+constexpr uint64_t OFF_LIT_LO = OFF_LIT_HI + LIT_TABLE_CDFS * CDF_BYTES;
+constexpr uint64_t OFF_LIT_CM = OFF_LIT_LO + LIT_TABLE_CDFS * CDF_BYTES;
+constexpr uint64_t LIT_CM_CDFS = 256 + 16 * 256;   // FirstNibble[ctx], SecondNibble[H + 16*ctx]  (codec/priors.rs:45-47)
+constexpr uint64_t OFF_CTYPE = OFF_LIT_CM + LIT_CM_CDFS * CDF_BYTES;
+constexpr uint64_t SLAB32_BYTES = 32 * CDF_BYTES;   // per-command-block-type / per-distance-prior slab
+constexpr uint64_t OFF_DPRIOR = OFF_CTYPE + 256 * SLAB32_BYTES;
+constexpr uint64_t OFF_MISC = OFF_DPRIOR + 256 * SLAB32_BYTES;
+constexpr uint64_t MISC_CDFS = 128;
+constexpr uint64_t OFF_LCM = OFF_MISC + MISC_CDFS * CDF_BYTES;   // literal context map (== the recycled PredictionMode buffer)
+constexpr uint64_t OFF_MIX = OFF_LCM + 16384;                     // mixing mask
+constexpr uint64_t OFF_DCM = OFF_MIX + 8192;                      // distance context map
+constexpr uint64_t OFF_SLOT_END = OFF_DCM + 1024;
+constexpr uint64_t SLOT_STRIDE = ((OFF_SLOT_END + 4095) / 4096) * 4096;
+
+// CTYPE slab entries (indexed by the current command block type)
+constexpr int CT_LL_COUNT_SMALL = 0, CT_LL_SIZE_BEG = 1, CT_LL_SIZE_LAST = 2, CT_LL_MANTISSA = 3;
+constexpr int CT_CP_COUNT_SMALL = 4;   // +index 0..15
+constexpr int CT_CP_COUNT_BEG = 20, CT_CP_COUNT_LAST = 21, CT_CP_COUNT_MANT = 22;   // +index 0..4
+constexpr int CT_DC_SIZE_BEG = 27, CT_DC_SIZE_LAST = 28;
+// DPRIOR slab entries (indexed by the distance context map value)
+constexpr int DP_DIST_BEG = 0;        // +index 0..8
+constexpr int DP_MNEMONIC = 16;       // +0..1
+constexpr int DP_DIST_LAST = 18, DP_DIST_MANT = 19;   // +0..4
+constexpr int DP_DICT_INDEX = 24;     // +0..4
+// MISC entries
+constexpr int MI_CC = 0;              // +last_4_states>>4
+constexpr int MI_TRANSFORM = 16;      // + i0 + 2*i1
+constexpr int MI_PRED = 48;           // + reference flat index 0..30 (codec/priors.rs:125-133)
+constexpr int MI_BTYPE = 80;          // + reference flat index 0..9 (codec/priors.rs:106-110)
+// PredictionModePriors flat offsets; DynamicContextMixingSpeed/PriorDepth are not listed in the reference's
+// define_prior_struct! and therefore alias ContextMapSpeedPalette[0] (src/priors.rs:226-236)
+constexpr int PM_ONLY = 0, PM_FIRST_NIBBLE = 2, PM_SECOND_NIBBLE = 4, PM_MNEMONIC = 6, PM_MIXING_VALUE = 10,
+              PM_SPEED_PALETTE = 27;
+constexpr int BT_MNEMONIC = 0, BT_FIRST = 3, BT_SECOND = 6, BT_STRIDE = 9;
+
+// named speeds (probability/interface.rs:321-328)
+#define DV_SPEED_MUD 0x10, 0x2000
+#define DV_SPEED_SLOW 0x20, 0x1000
+#define DV_SPEED_MED 0x30, 0x4000
+#define DV_SPEED_FAST 0x60, 0x4000
+#define DV_SPEED_PLANE 0x80, 0x4000
+#define DV_SPEED_ROCKET 0x180, 0x4000
+
+constexpr uint32_t NUM_SYMBOLS_BEFORE_FLUSH = 65536;   // ans.rs:57,138
+
+// brotli tables blob offsets (tools/gen_brotli_tables.py)
+constexpr uint32_t TB_SIZE_BITS = 24, TB_OFFSETS = 56, TB_CTX = 184, TB_TRANSFORMS = 2232, TB_PSMAP = 2616, TB_PS = 2744,
+                   TB_DICT = 3000, TB_DICT_SIZE = 122784, TB_TOTAL = 125784;
+
+enum : int32_t { ST_OK = 0, ST_NEED_INPUT = 1, ST_NEED_OUTPUT = 2, ST_FAIL = 3 };
+
+struct DecodeParams {
+    const uint8_t *in;
+    const uint64_t *in_off, *in_len;
+    uint8_t *out;
+    const uint64_t *out_off, *out_cap;
+    uint64_t *out_len;
+    int32_t *status;
+    const uint32_t *body_end;   // per stream: offset of the EOF marker (from the frame kernel); 0 = bad framing
+    uint32_t n_streams;
+    uint32_t *work_counter;
+    uint8_t *arena;             // n_slots * SLOT_STRIDE
+    const uint8_t *tables;      // brotli tables blob
+    uint64_t *nibble_counts;    // optional [2] totals (cmd, lit) for profiling
+};
+
+struct FrameParams {
+    const uint8_t *in;
+    const uint64_t *in_off, *in_len;
+    uint32_t *body_end;
+    int32_t *status;
+    uint32_t n_streams;
+    uint32_t flags;
+};
+
+}  // namespace dv

@@ -1,0 +1,15 @@
+// dv_kernels.h -- host-visible launch wrappers of the divANS kernels.
+#pragma once
+#include "dv_common.cuh"
+
+namespace dv {
+constexpr int DECODE_BLOCK_THREADS = 64;
+
+void launch_frame(const FrameParams &p, cudaStream_t st);
+void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
+void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
+cudaError_t upload_ctx_lut32(const uint8_t *host2048);
+cudaError_t upload_ctx_lut16(const uint8_t *host2048);
+int decode_max_blocks_per_sm32();
+int decode_max_blocks_per_sm16();
+}  // namespace dv

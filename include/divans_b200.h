@@ -1,0 +1,172 @@
+/*
+ * divans_b200.h -- C ABI of the B200-native divANS entropy engine (libdivans_b200.so).
+ *
+ * Two surfaces:
+ *  (1) the reference's own C FFI, symbol for symbol (reference: src/ffi/mod.rs, c/divans/ffi.h), so a
+ *      program written against libdivans links unchanged (c/example.c is the test client);
+ *  (2) a batch extension (ours, additive) -- the shape the GPU wants: N independent streams per call,
+ *      either from host buffers (end-to-end path, copies included) or device-resident.
+ *
+ * Every stream is decoded/encoded by hand-written sm_100a CUDA kernels; there is no CPU fallback:
+ * if no CUDA device / context can be had, constructors return NULL and batch calls return
+ * DIVANS_FAILURE after printing the CUDA error to stderr.
+ */
+#ifndef DIVANS_B200_H_
+#define DIVANS_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) reference FFI surface
+ * ------------------------------------------------------------------------------------------------ */
+typedef uint8_t DivansResult;                     /* reference: src/ffi/interface.rs:8-12 */
+#define DIVANS_SUCCESS ((uint8_t)0)
+#define DIVANS_NEEDS_MORE_INPUT ((uint8_t)1)
+#define DIVANS_NEEDS_MORE_OUTPUT ((uint8_t)2)
+#define DIVANS_FAILURE ((uint8_t)3)
+
+typedef uint8_t DivansOptionSelect;               /* reference: src/ffi/interface.rs:18-37 */
+#define DIVANS_OPTION_QUALITY 1
+#define DIVANS_OPTION_WINDOW_SIZE 2
+#define DIVANS_OPTION_LGBLOCK 3
+#define DIVANS_OPTION_DYNAMIC_CONTEXT_MIXING 4
+#define DIVANS_OPTION_USE_BROTLI_COMMAND_SELECTION 5
+#define DIVANS_OPTION_USE_BROTLI_BITSTREAM 6
+#define DIVANS_OPTION_USE_CONTEXT_MAP 7
+#define DIVANS_OPTION_LITERAL_ADAPTATION_CM_HIGH 8
+#define DIVANS_OPTION_FORCE_STRIDE_VALUE 9
+#define DIVANS_OPTION_STRIDE_DETECTION_QUALITY 10
+#define DIVANS_OPTION_PRIOR_DEPTH 11
+#define DIVANS_OPTION_LITERAL_ADAPTATION_STRIDE_HIGH 12
+#define DIVANS_OPTION_LITERAL_ADAPTATION_CM_LOW 13
+#define DIVANS_OPTION_LITERAL_ADAPTATION_STRIDE_LOW 14
+#define DIVANS_OPTION_BROTLI_LITERAL_BYTE_SCORE 15
+#define DIVANS_OPTION_SPEED_DETECTION_QUALITY 16
+#define DIVANS_OPTION_PRIOR_BITMASK_DETECTION 17
+#define DIVANS_OPTION_Q9_5 18
+#define DIVANS_OPTION_FORCE_LITERAL_CONTEXT_MODE 19
+#define DIVANS_OPTION_IR_OPTIMIZER 20
+
+struct CAllocator {                               /* reference: src/ffi/interface.rs:40-47 */
+    void *(*alloc_func)(void *opaque, size_t length);
+    void (*free_func)(void *opaque, void *mfd);
+    void *opaque;
+};
+struct DivansDecompressorState;
+struct DivansCompressorState;
+
+/* reference: src/ffi/mod.rs:178-187 (multithread=1, skip_crc=0) */
+struct DivansDecompressorState *divans_new_decompressor(void);
+/* reference: src/ffi/mod.rs:190-199 */
+struct DivansDecompressorState *divans_new_serial_decompressor(void);
+/* reference: src/ffi/mod.rs:213-232.  c/divans/ffi.h:61 declares only 2 arguments and c/example.c:62 calls it
+ * that way, so `multithread` may be garbage: it is ignored (output is identical either way). */
+struct DivansDecompressorState *divans_new_decompressor_with_custom_alloc(struct CAllocator alloc, uint8_t skip_crc,
+                                                                          uint8_t multithread);
+/* reference: src/ffi/mod.rs:236-262.  Streaming contract: offsets are cursors that are advanced; any call may
+ * return NEEDS_MORE_INPUT / NEEDS_MORE_OUTPUT and be resumed at byte granularity.  Implementation: input is
+ * buffered until the stream's 8-byte trailer has been seen, then the stream is decoded as a batch of one on
+ * the GPU and the output is streamed back out. */
+DivansResult divans_decode(struct DivansDecompressorState *state, const uint8_t *input_buf_ptr, size_t input_size,
+                           size_t *input_offset, uint8_t *output_buf_ptr, size_t output_size, size_t *output_offset);
+void divans_free_decompressor(struct DivansDecompressorState *mfd);          /* src/ffi/mod.rs:312-323 */
+uint8_t *divans_decompressor_malloc_u8(struct DivansDecompressorState *s, size_t n);          /* :276-283 */
+void divans_decompressor_free_u8(struct DivansDecompressorState *s, uint8_t *p, size_t n);     /* :285-292 */
+size_t *divans_decompressor_malloc_usize(struct DivansDecompressorState *s, size_t n);        /* :294-301 */
+void divans_decompressor_free_usize(struct DivansDecompressorState *s, size_t *p, size_t n);   /* :303-309 */
+
+struct DivansCompressorState *divans_new_compressor(void);                                     /* :18-27 */
+struct DivansCompressorState *divans_new_compressor_with_custom_alloc(struct CAllocator alloc); /* :38-52 */
+DivansResult divans_set_option(struct DivansCompressorState *state, DivansOptionSelect selector, uint32_t value); /* :58-67 */
+/* :70-91.  Input is buffered; the stream is produced by the GPU encoder at flush. */
+DivansResult divans_encode(struct DivansCompressorState *state, const uint8_t *input_buf_ptr, size_t input_size,
+                           size_t *input_offset, uint8_t *output_buf_ptr, size_t output_size, size_t *output_offset);
+DivansResult divans_encode_flush(struct DivansCompressorState *state, uint8_t *output_buf_ptr, size_t output_size,
+                                 size_t *output_offset);                                       /* :94-108 */
+void divans_free_compressor(struct DivansCompressorState *mfd);                                /* :111-122 */
+uint8_t *divans_compressor_malloc_u8(struct DivansCompressorState *s, size_t n);               /* :125-132 */
+void divans_compressor_free_u8(struct DivansCompressorState *s, uint8_t *p, size_t n);         /* :134-141 */
+size_t *divans_compressor_malloc_usize(struct DivansCompressorState *s, size_t n);             /* :143-150 */
+void divans_compressor_free_usize(struct DivansCompressorState *s, size_t *p, size_t n);       /* :152-169 */
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) batch extension
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct divans_b200_ctx divans_b200_ctx;
+
+#define DIVANS_B200_FLAG_SKIP_CRC 1u      /* same meaning as the reference's skip_crc (ffi/mod.rs:213) */
+#define DIVANS_B200_FLAG_NO_CRC_KERNEL 2u /* do not even run the CRC kernel (trailer magic still checked) */
+
+/* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
+
+/* device = CUDA ordinal; max_resident = cap on concurrently resident streams (0 = auto: sized to the GPU);
+ * lanes_per_stream = 32 (one warp owns one stream) or 16 (two streams share a warp); 0 = default (32). */
+divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream);
+void divans_b200_destroy(divans_b200_ctx *ctx);
+const char *divans_b200_last_error(divans_b200_ctx *ctx);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */
+uint64_t divans_b200_launch_count(divans_b200_ctx *ctx);
+/* device time of the most recent decode/encode kernel(s) in milliseconds (CUDA events on the context stream) */
+float divans_b200_last_kernel_ms(divans_b200_ctx *ctx);
+
+/* Decode n independent, complete .divans streams held in HOST memory.
+ * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]).
+ * Includes H2D of the inputs and D2H of outputs inside the call.  Returns DIVANS_SUCCESS if the batch ran
+ * (inspect status[] per stream), DIVANS_FAILURE on CUDA/context errors. */
+DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                           const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                           const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags);
+/* Same, all pointers are DEVICE pointers (inputs already resident in HBM, outputs left in HBM).
+ * `cuda_stream` is a cudaStream_t (NULL = the context's own stream).  Asynchronous: returns after enqueueing. */
+DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                             const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
+                                             const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
+                                             uint32_t flags, void *cuda_stream);
+DivansResult divans_b200_synchronize(divans_b200_ctx *ctx);
+
+/* Encoder options (subset of the reference's DivansCompressorOptions, src/interface.rs:444-484, that affects the
+ * entropy-coding half; command selection by the brotli crate is out of scope). */
+typedef struct {
+    int32_t window_size;            /* 10..24 */
+    int32_t dynamic_context_mixing; /* 0,1,2 */
+    int32_t prior_depth;
+    int32_t use_context_map;
+    int32_t force_stride;           /* 0..8, 9 = take the stride from the command */
+    int32_t have_literal_adaptation;
+    int16_t literal_adaptation[4][2];
+    int32_t literal_pred_mode;      /* internal literal-only compressor: LSB6=0 MSB6=1 UTF8=2 SIGN=3 */
+    int32_t literal_mixing_value;   /* internal literal-only compressor: value of all 8192 mixing entries (reference: 4) */
+} divans_b200_encode_options;
+void divans_b200_encode_options_default(divans_b200_encode_options *o);
+
+/* Encode n raw HOST buffers with the reference's internal literal-only command generator
+ * (src/raw_to_cmd/mod.rs:105-181): one PredictionMode command + Literal commands. */
+DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                           const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                           const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
+                                           const divans_b200_encode_options *opts);
+/* Encode n command lists ("DVCL" blobs, below) held in HOST memory: the entropy-coding half for arbitrary IR. */
+DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *blobs, const uint64_t *blob_off,
+                                                const uint64_t *blob_len, uint8_t *out, const uint64_t *out_off,
+                                                const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
+                                                const divans_b200_encode_options *opts);
+/*
+ * command list blob ("DVCL", little endian) -- the binary form of the reference's IR (src/bin/divans.rs:191-483):
+ *   u32 magic 0x4c435644, u32 version 1, u32 n_cmds, u32 n_predmodes, u32 n_literal_bytes, u32 window, u32[2] 0
+ *   n_cmds      x { u32 type, a, b, c, d }   type: 1 copy(a=distance,b=len) 2 dict(a=word_id,b=word_size,c=transform,d=final)
+ *                                                  3 literal(a=offset into literal pool,b=len,c=high_entropy)
+ *                                                  4/5/6 literal/command/distance block switch(a=type,b=stride) 7 prediction mode(a=index)
+ *   n_predmodes x { u8 pred_mode, u8 is_adv, u8 has_speeds, u8 0, u16 cm_speed[2][2], u16 stride_speed[2][2],
+ *                   u16 combined_speed[2][2], u16 lit_map_len, u16 dist_map_len, u8 lit_map[16384], u8 dist_map[1024],
+ *                   u8 mixing[8192] }
+ *   u8 literal pool[n_literal_bytes]
+ */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
