@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""bench.py -- the divANS batched-decode benchmark (BASELINE.json metric: decompressed MB/s on batched 64 KiB streams).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [...]                         the reference arm: the CPU decoder on the host cores
+
+A "step" = one pass of the hot path over one batch: every rank decodes its shard of independent streams
+(configs[1]: 4096 x 64 KiB synthetic-text streams per GPU; weak scaling: the per-GPU batch is fixed as N grows).
+`value` times K steps with inputs resident in HBM (CUDA events on the launching stream, max over ranks);
+`e2e` repeats the measurement through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed
+region).  `roofline` is computed for the stream-decode kernel from its own CUDA-event time; `cpu_baseline` times the
+CPU oracle (restatement of the reference algorithm; the Rust reference cannot be built in this image) on a bounded
+sample of the same streams.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAM_BYTES = 65536
+STREAMS_PER_GPU = 4096
+METRIC = "decompressed MB/s (batched 64KiB streams)"
+UNIT = "MB/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank, n_streams, engine=None):
+    """Synthetic-text streams of this rank's shard (seeded by global stream index) and their compressed form.
+    Compression is done by the product's own GPU encoder when it is available; the oracle is only the CPU baseline."""
+    from divans_b200 import synth
+    blob, off, ln = synth.text_streams(n_streams, STREAM_BYTES, seed=0xD1FA15 + 7919 * rank)
+    return blob, off, ln
+
+
+def encode_inputs(blob, off, ln, engine):
+    import divans_b200
+    n = len(off)
+    cap = np.full(n, STREAM_BYTES + STREAM_BYTES // 2 + 70144, np.uint64)
+    eoff = np.arange(n, dtype=np.uint64) * cap[0]
+    out = np.zeros(int(cap.sum()), np.uint8)
+    try:
+        out_len, status = engine.encode_batch_host(blob, off, ln, out, eoff, cap, divans_b200.encode_options())
+        assert (status == 0).all()
+        gen = "divans_b200 GPU encoder"
+    except divans_b200.DivansError:
+        # round-1 bring-up path (GPU encoder not in this build): inputs are prepared on the CPU, outside any timed region
+        from oracle import oracle_py as O
+        out, eoff, out_len = O.encode_batch(blob, off, ln, O.options(), os.cpu_count() or 4)
+        gen = "cpu oracle encoder (setup only, untimed)"
+    # compact to 16-byte aligned offsets
+    pad = (out_len + np.uint64(15)) & ~np.uint64(15)
+    coff = np.zeros(n, np.uint64)
+    coff[1:] = np.cumsum(pad)[:-1]
+    comp = np.zeros(int(pad.sum()) + 64, np.uint8)
+    for i in range(n):
+        comp[int(coff[i]): int(coff[i] + out_len[i])] = out[int(eoff[i]): int(eoff[i] + out_len[i])]
+    return comp, coff, out_len.astype(np.uint64), gen
+
+
+def cpu_baseline(comp, coff, clen, raw_blob, off, ln, n_sample, threads):
+    from oracle import oracle_py as O
+    n = min(n_sample, len(coff))
+    t0 = time.perf_counter()
+    out, out_len, status = O.decode_batch(comp, coff[:n], clen[:n], off[:n], ln[:n], threads)
+    dt = time.perf_counter() - t0
+    ok = bool((status == 0).all() and (out[: n * STREAM_BYTES] == raw_blob[: n * STREAM_BYTES]).all())
+    return {"value": n * STREAM_BYTES / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d of the benchmark's 64 KiB streams, oracle decode_batch, %.2f s" % (n, dt), "bit_exact_vs_input": ok}, out
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the Rust crate cannot be
+    compiled in this image) on all host threads, same workload/metric; bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_py as O
+    O.build()
+    threads = os.cpu_count() or 1
+    n_sample = int(os.environ.get("DIVANS_BENCH_REF_STREAMS", str(max(64, 16 * threads))))
+    blob, off, ln = make_inputs(0, n_sample)
+    enc, eoff, elen = O.encode_batch(blob, off, ln, O.options(), threads)
+    for _ in range(args.warmup):
+        O.decode_batch(enc, eoff, elen, off, ln, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, out_len, status = O.decode_batch(enc, eoff, elen, off, ln, threads)
+    dt = time.perf_counter() - t0
+    assert (status == 0).all() and (out[: blob.size] == blob).all()
+    v = args.steps * blob.size / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
+            "data": "synthetic", "config": {"workload": "%d x 64 KiB synthetic-text divANS streams (bounded sample of configs[1])" % n_sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d streams per step, all %d host threads" % (n_sample, threads)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("DIVANS_B200_LPS", "16")), help="lanes per stream: 32 or 16")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="streams in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import divans_b200
+    from divans_b200 import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    eng = divans_b200.Engine(local_rank, 0, args.lanes)
+    n = args.streams
+    blob, off, ln = make_inputs(rank, n)
+    comp, coff, clen, generator = encode_inputs(blob, off, ln, eng)
+    comp_bytes = int(clen.sum())
+    out_bytes = int(ln.sum())
+
+    # ---- device-resident arm ----
+    d_in = torch.from_numpy(comp).to(dev)
+    d_in_off = torch.from_numpy(coff.astype(np.int64)).to(dev)
+    d_in_len = torch.from_numpy(clen.astype(np.int64)).to(dev)
+    d_out = torch.zeros(out_bytes + 256, dtype=torch.uint8, device=dev)
+    d_out_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_out_cap = torch.from_numpy(ln.astype(np.int64)).to(dev)
+    d_out_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)          # a non-default stream: its handle is what the C ABI launches on
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        eng.decode_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
+                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, 0, stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    assert bool((d_status == 0).all()) and bool((d_out_len == STREAM_BYTES).all()), "decode failed"
+    assert bool((d_out[:out_bytes].cpu().numpy() == blob).all()), "GPU output differs from the original input"
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    # the decode kernel's own duration (CUDA events inside the library, on the same stream), one extra untimed pass
+    for _ in range(3):
+        step_device()
+        torch.cuda.synchronize()
+        main_ms.append(eng.last_main_kernel_ms())
+    kern_ms = float(np.median(main_ms))
+
+    # ---- end-to-end arm: host buffers (pinned), H2D + D2H inside the timed region, through the public host call ----
+    h_in = torch.from_numpy(comp).pin_memory()
+    h_out = torch.zeros(out_bytes + 256, dtype=torch.uint8).pin_memory()
+    h_in_np, h_out_np = h_in.numpy(), h_out.numpy()
+    for _ in range(2):
+        eng.decode_batch_host(h_in_np, coff, clen, h_out_np, off, ln)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        out_len_h, status_h = eng.decode_batch_host(h_in_np, coff, clen, h_out_np, off, ln)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert (status_h == 0).all() and (h_out_np[:out_bytes] == blob).all()
+
+    tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    uu = torch.tensor([float(out_bytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
+    total_out = float(uu[0])
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        value = total_out * args.steps / (dev_ms_max / 1e3) / 1e6
+        e2e_v = total_out * e2e_steps / (e2e_ms_max / 1e3) / 1e6
+        alg_bytes = comp_bytes + out_bytes     # per launch of the decode kernel on this rank (B_alg)
+        achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("decode_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i16/u64", "data": "synthetic",
+            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[1]), literal-only "
+                                   "encoding (1 PredictionMode + 1 Literal command)" % n,
+                       "streams_per_gpu": n, "stream_bytes": STREAM_BYTES, "compressed_bytes_per_gpu": comp_bytes,
+                       "lanes_per_stream": args.lanes, "parallelism": "dp%d (streams sharded, no data-path collective)" % world,
+                       "l2_policy": "inputs+outputs+model state per step (>0.39 GB + prior arena) exceed the 126 MB L2; no explicit flush",
+                       "input_generator": generator},
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": comp_bytes + 4 * 8 * n, "d2h_bytes_per_step": out_bytes + 12 * n,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "dv::decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
+        }
+        if not args.skip_cpu and world == 1:
+            threads = os.cpu_count() or 1
+            ns = args.cpu_sample or max(64, 16 * threads)
+            cb, cpu_out = cpu_baseline(comp, coff, clen, blob, off, ln, ns, threads)
+            nn = min(ns, n)
+            cb["gpu_bit_exact_vs_oracle"] = bool((cpu_out[: nn * STREAM_BYTES] == h_out_np[: nn * STREAM_BYTES]).all())
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

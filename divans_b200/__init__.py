@@ -34,7 +34,7 @@ REFERENCE_FFI_SYMBOLS = [
 ]
 BATCH_SYMBOLS = [
     "divans_b200_create", "divans_b200_destroy", "divans_b200_last_error", "divans_b200_launch_count",
-    "divans_b200_last_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
+    "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
     "divans_b200_encode_cmds_batch_host",
 ]
@@ -80,6 +80,8 @@ def load_library():
     L.divans_b200_launch_count.restype = ctypes.c_uint64
     L.divans_b200_last_kernel_ms.argtypes = [vp]
     L.divans_b200_last_kernel_ms.restype = ctypes.c_float
+    L.divans_b200_last_main_kernel_ms.argtypes = [vp]
+    L.divans_b200_last_main_kernel_ms.restype = ctypes.c_float
     L.divans_b200_synchronize.argtypes = [vp]
     L.divans_b200_synchronize.restype = ctypes.c_uint8
     batch = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -163,6 +165,9 @@ class Engine:
 
     def last_kernel_ms(self):
         return float(self._L.divans_b200_last_kernel_ms(self._h))
+
+    def last_main_kernel_ms(self):
+        return float(self._L.divans_b200_last_main_kernel_ms(self._h))
 
     def synchronize(self):
         if self._L.divans_b200_synchronize(self._h) != DIVANS_SUCCESS:

@@ -43,7 +43,7 @@ struct divans_b200_ctx {
     uint8_t *d_in = nullptr; size_t d_in_cap = 0;
     uint8_t *d_out = nullptr; size_t d_out_cap = 0;
     uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;   // in_off,in_len,out_off,out_cap,out_len (+status)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;   // ev0 | frame kernel | evm | decode kernel | ev1
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
     std::string err;
@@ -87,6 +87,7 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = ck(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               ck(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate") &&
+              ck(ctx, cudaEventCreate(&ctx->evm), "cudaEventCreate") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_tables, TB_TOTAL), "cudaMalloc(tables)") &&
               ck(ctx, cudaMemcpy(ctx->d_tables, dv_tables_blob, TB_TOTAL, cudaMemcpyHostToDevice), "cudaMemcpy(tables)") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_counter, 64), "cudaMalloc(counter)") &&
@@ -116,6 +117,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     cudaFree(ctx->d_body_end); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evm) cudaEventDestroy(ctx->evm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -126,6 +128,12 @@ extern "C" float divans_b200_last_kernel_ms(divans_b200_ctx *ctx) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
     return ctx->last_kernel_ms;
+}
+extern "C" float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx) {
+    if (!ctx) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->evm, ctx->ev1) != cudaSuccess) return -1.f;
+    return ms;
 }
 extern "C" DivansResult divans_b200_synchronize(divans_b200_ctx *ctx) {
     if (!ctx) return DIVANS_FAILURE;
@@ -168,6 +176,7 @@ extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, si
     CK(cudaEventRecord(ctx->ev0, st));
     launch_frame(fp, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
+    CK(cudaEventRecord(ctx->evm, st));
     if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));

@@ -112,6 +112,8 @@ const char *divans_b200_last_error(divans_b200_ctx *ctx);
 uint64_t divans_b200_launch_count(divans_b200_ctx *ctx);
 /* device time of the most recent decode/encode kernel(s) in milliseconds (CUDA events on the context stream) */
 float divans_b200_last_kernel_ms(divans_b200_ctx *ctx);
+/* device time of the dominant kernel alone (stream decoder / encoder model pass) of the most recent call */
+float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx);
 
 /* Decode n independent, complete .divans streams held in HOST memory.
  * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]).

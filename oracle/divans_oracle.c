@@ -291,8 +291,14 @@ static const prior_ent T_PM[] = {{PM_Only, 1, {1}}, {PM_LiteralSpeed, 1, {1}}, {
                                  {PM_Mnemonic, 1, {4}}, {PM_PriorMixingValue, 1, {17}}, {PM_ContextMapSpeedPalette, 1, {4}}};
 #define NEL(a) ((int)(sizeof(a) / sizeof((a)[0])))
 
+/* The two 3*256*256 literal tables (6 MB each) are recycled per thread: the reference allocates and default-initialises
+ * them per decompressor object (codec/interface.rs:728-729); we keep the initialisation (it is part of the reference's
+ * cost) but not the mmap/munmap churn, which would understate the CPU baseline on many-core hosts. */
+static __thread dvo_cdf16 *tl_pool[2];
 static dvo_cdf16 *alloc_priors(size_t n) {
-    dvo_cdf16 *p = (dvo_cdf16 *)malloc(n * sizeof(dvo_cdf16));
+    dvo_cdf16 *p = NULL;
+    if (n == 3u * 256 * 256) { for (int i = 0; i < 2; i++) if (tl_pool[i]) { p = tl_pool[i]; tl_pool[i] = NULL; break; } }
+    if (!p) p = (dvo_cdf16 *)malloc(n * sizeof(dvo_cdf16));
     dvo_cdf16 d; dvo_cdf_default(&d);
     for (size_t i = 0; i < n; i++) p[i] = d;
     return p;
@@ -543,7 +549,9 @@ static void codec_init(codec *s, int window, int encoding) {
 }
 static void codec_free(codec *s) {
     free(s->lit_len_priors); free(s->cc_priors); free(s->copy_priors); free(s->dict_priors); free(s->pred_priors);
-    free(s->btype_priors); free(s->lit_high_priors); free(s->lit_low_priors); free(s->lit_cm_priors); free(s->rc.ring);
+    free(s->btype_priors); free(s->lit_cm_priors); free(s->rc.ring);
+    { dvo_cdf16 *big[2] = {s->lit_high_priors, s->lit_low_priors};
+      for (int k = 0; k < 2; k++) { int put = 0; for (int i = 0; i < 2 && !put; i++) if (!tl_pool[i]) { tl_pool[i] = big[k]; put = 1; } if (!put) free(big[k]); } }
     if (s->cmd.encoding) { ans_enc_free(&s->cmd.e); ans_enc_free(&s->lit.e); }
 }
 #define P(tbl, T, type, i0, i1, i2) (&(tbl)[prior_index(T, NEL(T), type, i0, i1, i2)])
@@ -1439,6 +1447,7 @@ static void *batch_worker(void *arg) {
         }
         j->out_len[i] = ol; j->status[i] = rc;
     }
+    for (int i = 0; i < 2; i++) { free(tl_pool[i]); tl_pool[i] = NULL; }
     return NULL;
 }
 static int run_batch(batch_job *j, int n_threads) {

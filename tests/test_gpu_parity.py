@@ -1,0 +1,185 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact bar (integer/byte path)."""
+import hashlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_and_compare(engine, oracle, streams, raws=None, flags=0):
+    caps = [(len(r) if r is not None else 1 << 20) + 64 for r in (raws or [None] * len(streams))]
+    res = engine.decode(streams, caps, flags)
+    for i, (st, out) in enumerate(res):
+        rc, ref = oracle.decode(streams[i], out_cap=caps[i])
+        assert rc == 0, "oracle failed on stream %d" % i
+        assert st == 0, "gpu status %d on stream %d" % (st, i)
+        assert out == ref, "stream %d: first diff at %d" % (i, next((k for k in range(min(len(out), len(ref))) if out[k] != ref[k]), -1))
+        if raws and raws[i] is not None:
+            assert out == raws[i]
+
+
+@pytest.fixture(scope="module")
+def text():
+    from divans_b200 import synth
+    return synth.text_corpus(1 << 20)
+
+
+def test_golden_fixtures(engine, oracle, golden):
+    streams = [open(e["path"], "rb").read() for e in golden]
+    res = engine.decode(streams, [e["raw_len"] + 64 for e in golden])
+    for e, (st, out) in zip(golden, res):
+        assert st == 0 and len(out) == e["raw_len"], e["name"]
+        assert hashlib.sha256(out).hexdigest() == e["raw_sha256"], e["name"]   # == the reference's raw testdata file
+
+
+def test_golden_fixtures_one_warp_per_stream(engine32, oracle, golden):
+    streams = [open(e["path"], "rb").read() for e in golden]
+    res = engine32.decode(streams, [e["raw_len"] + 64 for e in golden])
+    for e, (st, out) in zip(golden, res):
+        assert st == 0 and hashlib.sha256(out).hexdigest() == e["raw_sha256"], e["name"]
+
+
+def test_edge_lengths_literal_only(engine, oracle, text):
+    raws = [text[:n] for n in [0, 1, 2, 7, 8, 9, 14, 15, 16, 17, 255, 4097, 32767, 32768, 32769, 70001]] + [bytes(range(256)) * 5]
+    for win in [10, 22]:
+        _decode_and_compare(engine, oracle, [oracle.encode_raw(r, oracle.options(window_size=win)) for r in raws], raws)
+
+
+@pytest.mark.parametrize("pm", [0, 1, 2, 3])
+def test_prediction_modes_and_mixing_values(engine, oracle, text, pm):
+    raws, streams = [], []
+    for mv in range(9):
+        r = text[7000 * mv: 7000 * mv + 5000]
+        blob = np.frombuffer(r, np.uint8)
+        out, off, ln = oracle.encode_batch(blob, [0], [len(r)], oracle.options(), 1, False, pm, mv)
+        raws.append(r)
+        streams.append(out[: int(ln[0])].tobytes())
+    _decode_and_compare(engine, oracle, streams, raws)
+
+
+@pytest.mark.parametrize("mixing", [1, 2, 3])
+def test_dynamic_context_mixing(engine, oracle, text, mixing):
+    raws, streams = [], []
+    for mv in [0, 1, 2, 3, 4, 6]:
+        r = text[3000 * mv: 3000 * mv + 9000]
+        blob = np.frombuffer(r, np.uint8)
+        out, off, ln = oracle.encode_batch(blob, [0], [len(r)], oracle.options(dynamic_context_mixing=mixing), 1, False, 2, mv)
+        raws.append(r)
+        streams.append(out[: int(ln[0])].tobytes())
+    _decode_and_compare(engine, oracle, streams, raws)
+
+
+def test_lz77_copies_and_window_wrap(engine, oracle, text):
+    rng = np.random.default_rng(9)
+    base = rng.integers(97, 105, 3000).astype(np.uint8).tobytes()
+    raws = [text[:20000], text[3000:70000], text[:300] * 50, base * 30, b"a" * 5000, b"ab" * 4000]
+    for win in [10, 12, 16, 22]:
+        streams = [oracle.Commands.lz77(r, window=win).encode(oracle.options(window_size=win, dynamic_context_mixing=2 if win == 12 else 0))
+                   for r in raws]
+        _decode_and_compare(engine, oracle, streams, raws)
+
+
+def test_random_ir_fuzz(engine, oracle, text):
+    import irfuzz
+    streams = []
+    for seed in range(40):
+        ir = irfuzz.random_ir(oracle, seed, n_cmds=150, window=[10, 14, 16, 22][seed % 4], text=text)
+        c = oracle.Commands.from_ir(ir)
+        o = oracle.options(window_size=c.window, dynamic_context_mixing=seed % 3, use_context_map=0 if seed % 7 == 3 else 1,
+                           force_stride=9 if seed % 5 else 3, prior_depth=seed % 4)
+        streams.append(c.encode(o))
+    _decode_and_compare(engine, oracle, streams)
+
+
+def test_random_ir_fuzz_one_warp_per_stream(engine32, oracle, text):
+    import irfuzz
+    streams = []
+    for seed in range(100, 112):
+        c = oracle.Commands.from_ir(irfuzz.random_ir(oracle, seed, n_cmds=100, window=16, text=text))
+        streams.append(c.encode(oracle.options(window_size=16, dynamic_context_mixing=seed % 3)))
+    _decode_and_compare(engine32, oracle, streams)
+
+
+def test_chunk_restart_every_65536_symbols(engine, oracle):
+    # > 65536 literal nibbles and > 65536 command nibbles per coder (ans.rs:236,138)
+    rng = np.random.default_rng(4)
+    raw = rng.integers(0, 256, 150000).astype(np.uint8).tobytes()       # 300k literal nibbles, incompressible
+    s1 = oracle.encode_raw(raw)
+    rep = (b"abcdefgh" * 3 + b"xyz") * 40000                                # > 65536 command nibbles from many short copies
+    s2 = oracle.Commands.lz77(rep[:600000], window=16).encode(oracle.options(window_size=16))
+    _decode_and_compare(engine, oracle, [s1, s2], [raw, rep[:600000]])
+
+
+def test_status_codes(engine, oracle, text):
+    raw = text[:30000]
+    enc = oracle.encode_raw(raw)
+    cut = [enc[:5], enc[:16], enc[:40], enc[: len(enc) - 9], enc[: len(enc) - 1]]
+    res = engine.decode(cut, [len(raw) + 64] * len(cut))
+    assert all(st == 1 for st, _ in res), [st for st, _ in res]                       # NEEDS_MORE_INPUT
+    bad_magic = b"\x00" + enc[1:]
+    bad_window = enc[:5] + b"\x09" + enc[6:]
+    flipped = bytearray(enc); flipped[len(enc) // 2] ^= 0x40
+    bad_tail = enc[:-1] + b"!"
+    res = engine.decode([bad_magic, bad_window, bytes(flipped), bad_tail, enc], [len(raw) + 64] * 5)
+    assert [st for st, _ in res] == [3, 3, 3, 3, 0]
+    # skip_crc: trailer CRC bytes ignored, "ans~" still required (codec/decoder.rs:204-210)
+    wrong_crc = enc[:-8] + b"\x00\x00\x00\x00" + enc[-4:]
+    res = engine.decode([wrong_crc, bad_tail], [len(raw) + 64] * 2, flags=1)
+    assert res[0][0] == 0 and res[0][1] == raw and res[1][0] == 3
+    # output capacity too small
+    res = engine.decode([enc], [100])
+    assert res[0][0] == 2
+    # a failing stream must not poison its batch
+    res = engine.decode([enc, bytes(flipped), enc], [len(raw) + 64] * 3)
+    assert [st for st, _ in res] == [0, 3, 0] and res[0][1] == raw and res[2][1] == raw
+
+
+def test_reference_ffi_streaming_reader(oracle, golden):
+    # BASELINE config 1: alice29 through DivansDecompressorReader / divans_decode with the buffer sizes the reference's
+    # integration tests use (src/bin/integration_test.rs:270-272: 65536 / 15 / 1)
+    import divans_b200
+    e = [g for g in golden if g["name"] == "alice29_literal_only"][0]
+    enc = open(e["path"], "rb").read()
+    for name in ["alice29_literal_only", "alice29_priors_mix2"]:
+        e = [g for g in golden if g["name"] == name][0]
+        enc = open(e["path"], "rb").read()
+        for bs in [65536, 4096, 15, 1]:
+            rd = divans_b200.DivansDecompressorReader(io.BytesIO(enc), bs, False, True)
+            out = bytearray()
+            chunk = bytearray(bs if bs > 1 else 1)
+            while True:
+                n = rd.readinto(chunk)
+                if not n:
+                    break
+                out += chunk[:n]
+            rd.close()
+            assert hashlib.sha256(bytes(out)).hexdigest() == e["raw_sha256"], (name, bs)
+    # truncated input -> UnexpectedEof, corrupt -> InvalidData (src/reader.rs:96-98,279-281)
+    rd = divans_b200.DivansDecompressorReader(io.BytesIO(enc[:-3]), 4096)
+    with pytest.raises(EOFError):
+        rd.readinto(bytearray(1 << 20))
+    bad = bytearray(enc); bad[100] ^= 1
+    rd = divans_b200.DivansDecompressorReader(io.BytesIO(bytes(bad)), 4096)
+    with pytest.raises(ValueError):
+        rd.readinto(bytearray(1 << 20))
+
+
+def test_full_size_batch_roundtrip_property(engine, oracle):
+    # BASELINE config 2 size: 4096 independent 64 KiB streams; size-independent property = encode -> decode identity,
+    # plus a sample of streams checked byte for byte against the oracle's decode
+    from divans_b200 import synth
+    n = 4096
+    blob, off, ln = synth.text_streams(n, 65536)
+    enc, eoff, elen = oracle.encode_batch(blob, off, ln, oracle.options(), os.cpu_count() or 4)
+    out = np.zeros(blob.size + 256, np.uint8)
+    out_len, status = engine.decode_batch_host(enc, eoff, elen, out, off, ln)
+    assert (status == 0).all() and (out_len == 65536).all()
+    assert (out[: blob.size] == blob).all()
+    pick = [0, 1, 17, 2047, 4095]
+    for i in pick:
+        rc, ref = oracle.decode(enc[int(eoff[i]): int(eoff[i] + elen[i])].tobytes(), out_cap=65600)
+        assert rc == 0 and ref == out[int(off[i]): int(off[i]) + 65536].tobytes()
