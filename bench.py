@@ -200,7 +200,7 @@ def main():
 
     def step_device():
         eng.decode_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
-                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, 0, stream.cuda_stream)
+                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, d_in.numel(), 0, stream.cuda_stream)
 
     def barrier():
         if world > 1:

@@ -87,7 +87,7 @@ def load_library():
     batch = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     L.divans_b200_decode_batch_host.argtypes = batch + [ctypes.c_uint32]
     L.divans_b200_decode_batch_host.restype = ctypes.c_uint8
-    L.divans_b200_decode_batch_device.argtypes = batch + [ctypes.c_uint32, vp]
+    L.divans_b200_decode_batch_device.argtypes = batch + [ctypes.c_uint64, ctypes.c_uint32, vp]
     L.divans_b200_decode_batch_device.restype = ctypes.c_uint8
     L.divans_b200_encode_options_default.argtypes = [ctypes.POINTER(EncodeOptions)]
     L.divans_b200_encode_batch_host.argtypes = batch + [ctypes.POINTER(EncodeOptions)]
@@ -189,10 +189,10 @@ class Engine:
             raise DivansError("decode_batch_host: " + self._err())
         return out_len, status
 
-    def decode_batch_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, n, flags=0, stream=None):
+    def decode_batch_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, n, in_total_bytes, flags=0, stream=None):
         """All arguments are raw device pointers (ints), e.g. ``tensor.data_ptr()``.  Asynchronous."""
         rc = self._L.divans_b200_decode_batch_device(self._h, n, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status,
-                                                     flags, stream)
+                                                     int(in_total_bytes), flags, stream)
         if rc != DIVANS_SUCCESS:
             raise DivansError("decode_batch_device: " + self._err())
 

@@ -39,7 +39,8 @@ struct divans_b200_ctx {
     uint32_t *d_counter = nullptr;
     uint64_t *d_nibbles = nullptr;
     // grow-only scratch
-    uint32_t *d_body_end = nullptr; size_t body_end_cap = 0;
+    uint32_t *d_frame = nullptr; size_t frame_cap = 0;
+    uint8_t *d_payload = nullptr; size_t payload_cap = 0;
     uint8_t *d_in = nullptr; size_t d_in_cap = 0;
     uint8_t *d_out = nullptr; size_t d_out_cap = 0;
     uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;   // in_off,in_len,out_off,out_cap,out_len (+status)
@@ -114,7 +115,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_arena); cudaFree(ctx->d_tables); cudaFree(ctx->d_counter); cudaFree(ctx->d_nibbles);
-    cudaFree(ctx->d_body_end); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_frame); cudaFree(ctx->d_payload); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evm) cudaEventDestroy(ctx->evm);
@@ -152,7 +153,7 @@ static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
 extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                                         const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
                                                         const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
-                                                        uint32_t flags, void *cuda_stream) {
+                                                        uint64_t in_total_bytes, uint32_t flags, void *cuda_stream) {
     if (!ctx) return DIVANS_FAILURE;
     if (n == 0) return DIVANS_SUCCESS;
     if (n > 0xffffffffull) { ctx->err = "too many streams"; return DIVANS_FAILURE; }
@@ -162,25 +163,26 @@ extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, si
     uint32_t resident = (uint32_t)(n < ctx->max_resident ? n : ctx->max_resident);
     uint32_t blocks = (resident + gpb - 1) / gpb;
     if (ensure_arena(ctx, (size_t)blocks * gpb) != DIVANS_SUCCESS) return DIVANS_FAILURE;
-    if (!grow(ctx, &ctx->d_body_end, &ctx->body_end_cap, n)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_frame, &ctx->frame_cap, 4 * n)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_payload, &ctx->payload_cap, (size_t)in_total_bytes + 48 * n + 64)) return DIVANS_FAILURE;
     CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
     FrameParams fp;
-    fp.in = d_in; fp.in_off = d_in_off; fp.in_len = d_in_len; fp.body_end = ctx->d_body_end; fp.status = d_status;
+    fp.in = d_in; fp.in_off = d_in_off; fp.in_len = d_in_len; fp.frame = ctx->d_frame; fp.status = d_status;
     fp.n_streams = (uint32_t)n; fp.flags = flags;
     DecodeParams dp;
     dp.in = d_in; dp.in_off = d_in_off; dp.in_len = d_in_len; dp.out = d_out; dp.out_off = d_out_off; dp.out_cap = d_out_cap;
-    dp.out_len = d_out_len; dp.status = d_status; dp.body_end = ctx->d_body_end; dp.n_streams = (uint32_t)n;
+    dp.out_len = d_out_len; dp.status = d_status; dp.frame = ctx->d_frame; dp.payload = ctx->d_payload; dp.n_streams = (uint32_t)n;
     dp.work_counter = ctx->d_counter; dp.arena = ctx->d_arena; dp.tables = ctx->d_tables; dp.nibble_counts = ctx->d_nibbles;
     static const bool dbg = getenv("DIVANS_B200_DEBUG") != nullptr;
     static const bool skip_decode = getenv("DIVANS_B200_SKIP_DECODE") != nullptr;
     CK(cudaEventRecord(ctx->ev0, st));
-    launch_frame(fp, st);
+    launch_frame(fp, ctx->d_payload, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
     if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
-    ctx->launches += 2;
+    ctx->launches += skip_decode ? 3 : 4;
     CK(cudaGetLastError());
     return DIVANS_SUCCESS;
 }
@@ -210,7 +212,7 @@ extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size
     CK(cudaMemcpyAsync(m + 3 * n, out_cap, n * 8, cudaMemcpyHostToDevice, st));
     int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
     DivansResult r = divans_b200_decode_batch_device(ctx, n, ctx->d_in, m, m + n, ctx->d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
-                                                     flags, st);
+                                                     in_end, flags, st);
     if (r != DIVANS_SUCCESS) return r;
     CK(cudaMemcpyAsync(out_len, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));

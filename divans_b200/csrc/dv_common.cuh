@@ -79,7 +79,8 @@ struct DecodeParams {
     const uint64_t *out_off, *out_cap;
     uint64_t *out_len;
     int32_t *status;
-    const uint32_t *body_end;   // per stream: offset of the EOF marker (from the frame kernel); 0 = bad framing
+    const uint32_t *frame;      // per stream [4]: body_end, cmd payload bytes, lit payload bytes, payload base offset (frame kernel)
+    const uint8_t *payload;     // compacted per-coder byte streams (demux kernel)
     uint32_t n_streams;
     uint32_t *work_counter;
     uint8_t *arena;             // n_slots * SLOT_STRIDE
@@ -90,10 +91,13 @@ struct DecodeParams {
 struct FrameParams {
     const uint8_t *in;
     const uint64_t *in_off, *in_len;
-    uint32_t *body_end;
+    uint32_t *frame;            // per stream [4]: body_end, cmd payload bytes, lit payload bytes, reserved
     int32_t *status;
     uint32_t n_streams;
     uint32_t flags;
 };
+
+// payload placement: stream i's two compacted byte streams live at payload + base(i): cmd first, lit at +align16(cmd bytes)
+__host__ __device__ inline uint64_t payload_base(uint64_t in_off, uint32_t i) { return (in_off + 48ull * i + 15ull) & ~15ull; }
 
 }  // namespace dv

@@ -1,5 +1,5 @@
 // dv_kernels.cu -- sm_100a kernels of the divANS batch engine: framing/CRC pre-pass and the stream decoder.
-#include "dv_codec.cuh"
+#include "dv_engine_kernel.cuh"
 #include "dv_kernels.h"
 
 namespace dv {
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
     const uint8_t *in = p.in + p.in_off[sidx];
     uint64_t n = p.in_len[sidx];
     int32_t st = ST_OK;
-    uint32_t body_end = 0;
+    uint32_t body_end = 0, pay0 = 0, pay1 = 0;
     if (n < 16) st = ST_NEED_INPUT;
     else if (in[0] != 0xff || in[1] != 0xe5 || in[2] != 0x8c || in[3] != 0x9f) st = ST_FAIL;   // MAGIC_NUMBER, src/interface.rs:164
     else if (in[5] < 10 || in[5] >= 25) st = ST_FAIL;                                             // BadWindowSize, divans_decompressor.rs:47-50
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
             if (b < 16) { if (pos + 3 > n) { st = ST_NEED_INPUT; break; } len = ((uint64_t)in[pos + 1] | ((uint64_t)in[pos + 2] << 8)) + 1; hdr = 3; }
             else { uint32_t k = b >> 4; if (k > 3) { st = ST_FAIL; break; } len = 1024ull << (k << 1); hdr = 1; }
             if (pos + hdr + len > n) { st = ST_NEED_INPUT; break; }
+            if (b & 1) pay1 += (uint32_t)len; else pay0 += (uint32_t)len;
             pos += hdr + len;
         }
         if (st == ST_OK) {
@@ -72,120 +73,231 @@ __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
             }
         }
     }
-    p.body_end[sidx] = st == ST_OK ? body_end : 0;
+    p.frame[4 * sidx + 0] = st == ST_OK ? body_end : 0;
+    p.frame[4 * sidx + 1] = st == ST_OK ? pay0 : 0;
+    p.frame[4 * sidx + 2] = st == ST_OK ? pay1 : 0;
     p.status[sidx] = st;
 }
+
+// exclusive scan of the per-stream payload footprints -> frame[4i+3] = base of stream i's compacted payload (16-byte units)
+__global__ void __launch_bounds__(1024) payload_scan_kernel(uint32_t *frame, uint32_t n) {
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t lo = min(n, t * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += ((frame[4 * i + 1] + 15) >> 4) + ((frame[4 * i + 2] + 15) >> 4) + 1;
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t base = part[t] - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        frame[4 * i + 3] = base;
+        base += ((frame[4 * i + 1] + 15) >> 4) + ((frame[4 * i + 2] + 15) >> 4) + 1;
+    }
+}
+
+// demux (mux.rs:384-444): one warp per stream copies the payload of every record to the stream's compact area:
+// command-coder bytes at base, literal-coder bytes at base + align16(cmd bytes)
+__global__ void __launch_bounds__(128) demux_kernel(FrameParams p, uint8_t *payload) {
+    const uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (sidx >= p.n_streams || p.status[sidx] != ST_OK) return;
+    const uint8_t *in = p.in + p.in_off[sidx];
+    const uint32_t body_end = p.frame[4 * sidx + 0];
+    uint8_t *dst0 = payload + 16ull * p.frame[4 * sidx + 3];
+    uint8_t *dst1 = dst0 + (((uint64_t)p.frame[4 * sidx + 1] + 15) & ~15ull);
+    uint32_t pos = 16;
+    while (pos < body_end) {
+        uint32_t b = in[pos], len, hdr;
+        if (b < 16) { len = ((uint32_t)in[pos + 1] | ((uint32_t)in[pos + 2] << 8)) + 1; hdr = 3; }
+        else { len = 1024u << ((b >> 4) << 1); hdr = 1; }
+        const uint8_t *src = in + pos + hdr;
+        uint8_t *d = (b & 1) ? dst1 : dst0;
+        // byte head to a 4-byte aligned destination, then words assembled from (possibly unaligned) source bytes
+        uint32_t head = min(len, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
+        if (lane < head) d[lane] = src[lane];
+        uint32_t nw = (len - head) >> 2;
+        const uint8_t *s2 = src + head; uint32_t *d2 = reinterpret_cast<uint32_t *>(d + head);
+        const uint32_t *sa = reinterpret_cast<const uint32_t *>((uintptr_t)s2 & ~(uintptr_t)3);
+        const uint32_t sh = ((uint32_t)(uintptr_t)s2 & 3u) * 8u;
+        for (uint32_t i = lane; i < nw; i += 32) d2[i] = __funnelshift_r(sa[i], sa[i + 1], sh);   // over-read <= 3 B stays inside the stream (EOF marker + trailer follow)
+        uint32_t tail = (len - head) & 3;
+        if (lane < tail) d[head + 4 * nw + lane] = src[head + 4 * nw + lane];
+        if (b & 1) dst1 += len; else dst0 += len;
+        pos += hdr + len;
+    }
+}
+
 
 #endif  // DV_LPS == 32 (frame kernel)
 
 // ---------------------------------------------------------------------------------------------------------------
-// decode kernel: persistent lane-groups pull stream indices from a global counter.
+// stream kernel: persistent warps, two streams per warp in lock step (dv_engine.cuh), work pulled from a global counter.
+// LPS == 32 keeps the north-star "one warp owns one stream" layout: the upper half-warp mirrors the lower one.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SMEM_WORDS_PER_GROUP = 96;   // 65 bitmap words (padded to 80) + 64 B dictionary scratch
+constexpr int SMEM_BYTES_PER_GROUP = (int)((sizeof(Cold) + 15) / 16 * 16);
 
-template <int LPS>   // lanes per stream: 32 (upper half mirrors) or 16 (two streams per warp)
+// The converged nibble core.  Every lane of the warp executes it every iteration, unpredicated: a group without work
+// codes against its slot's dummy CDF with a parked coder (no memory side effects that matter).
+template <bool ENC, int LPS>
+__device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, const bool writer) {
+    const Grp gg = {FULL, g.shift, g.l16, writer, false, g.store0};
+    const int c = nx.cdf[g.l16], maxv = nx.cdf[15];
+    const int inc = (int)(short)(nx.speed & 0xffff), lim = nx.speed >> 16;
+    int sym, start, freq;
+    if (!__any_sync(FULL, nx.cdf2 != nullptr)) {
+        if (!ENC) {
+            coder_fill(s.cur);
+            int off = (int)(s.cur.a & 0x7fff);
+            int r = (int)(short)((off * maxv) >> 15);                       // probability/interface.rs:140
+            bool pred = (g.l16 == 15) || (r < c);
+            unsigned bal = __ballot_sync(FULL, pred);
+            sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
+        } else sym = nx.sym;
+        int cum = cdf_div(c, maxv);
+        int hi = __shfl_sync(FULL, cum, sym, 16);
+        int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
+        if (sym == 0) lo = 0;
+        start = (int)(short)(lo + 1); freq = (int)(short)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
+        if (!ENC) coder_advance(s.cur, start, freq);
+        else { if (g.store0) const_cast<uint32_t *>(s.cur.p)[s.cur.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); s.cur.left++; }
+        int c2 = cdf_blend(gg, c, maxv, sym, inc, lim);
+        if (writer) nx.cdf[g.l16] = (int16_t)c2;
+        return sym;
+    }
+    // ---- at least one group mixes two priors (dynamic context mixing >= 2, codec/literal.rs:219-243) ----
+    const bool mixg = nx.cdf2 != nullptr;
+    int cc = c, mc = maxv;
+    if (mixg) { cc = nx.cdf2[g.l16]; mc = nx.cdf2[15]; }
+    Weights w = nx.mix_hi ? s.c->w_hi : s.c->w_lo;
+    int prod = mc * maxv;
+    int lz = prod == 0 ? 32 : __clz(prod); if (lz > 17) lz = 17;
+    int shift = 17 - lz;
+    int mixr = w.norm, inv = (1 << 15) - mixr;
+    int rs = (cc * maxv) >> shift, ro = (c * mc) >> shift;
+    int ca = (int)(short)((int)((unsigned)rs * (unsigned)mixr + (unsigned)ro * (unsigned)inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
+    int ma = __shfl_sync(FULL, ca, 15, 16);
+    int cu = mixg ? ca : c, mu = mixg ? ma : maxv;
+    if (!ENC) {
+        coder_fill(s.cur);
+        int off = (int)(s.cur.a & 0x7fff);
+        int r = (int)(short)((off * mu) >> 15);
+        bool pred = (g.l16 == 15) || (r < cu);
+        unsigned bal = __ballot_sync(FULL, pred);
+        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
+    } else sym = nx.sym;
+    int cum = cdf_div(cu, mu);
+    int hi = __shfl_sync(FULL, cum, sym, 16);
+    int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
+    if (sym == 0) lo = 0;
+    start = (int)(short)(lo + 1); freq = (int)(short)(hi - lo - 1);
+    int f_cm = cdf_freq(gg, cc, mc, sym);
+    int f_nb = cdf_freq(gg, c, maxv, sym);
+    if (!ENC) coder_advance(s.cur, start, freq);
+    else { if (g.store0) const_cast<uint32_t *>(s.cur.p)[s.cur.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); s.cur.left++; }
+    if (mixg) {
+        weights_update(w, f_cm, f_nb, freq);
+        if (nx.mix_hi) s.c->w_hi = w; else s.c->w_lo = w;
+        const int sp = nx.mix_hi ? s.c->ad_cm_hi : s.c->ad_cm_lo;
+        int c2 = cdf_blend(gg, cc, mc, sym, (int)(short)(sp & 0xffff), sp >> 16);
+        if (writer) nx.cdf2[g.l16] = (int16_t)c2;
+    }
+    int s2 = cdf_blend(gg, c, maxv, sym, inc, lim);
+    if (writer) nx.cdf[g.l16] = (int16_t)s2;
+    return sym;
+}
+
+template <int LPS>
 __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodeParams p) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     constexpr int GPW = 32 / LPS;
     const int group_in_warp = (LPS == 16) ? (lane >> 4) : 0;
     const int group_in_block = warp_in_block * GPW + group_in_warp;
     const uint32_t slot = blockIdx.x * (DECODE_BLOCK_THREADS / LPS) + group_in_block;
-    Grp g;
+    G2 g;
     g.l16 = lane & 15;
     g.shift = (LPS == 16) ? (lane & 16) : 0;
-    g.mask = (LPS == 16) ? (0xffffu << (lane & 16)) : 0xffffffffu;
-    g.writer = (LPS == 16) ? true : (lane < 16);
-    g.lane0 = (lane & 15) == 0;
+    g.gmask = (LPS == 16) ? (0xffffu << (lane & 16)) : 0xffffffffu;
     g.store0 = (LPS == 16) ? ((lane & 15) == 0) : (lane == 0);
+    const bool writer = (LPS == 16) ? true : (lane < 16);
 
-    Stream s;
-    uint8_t *slotp = p.arena + (uint64_t)slot * SLOT_STRIDE;
-    s.lit_hi = reinterpret_cast<int16_t *>(slotp + OFF_LIT_HI);
-    s.lit_lo = reinterpret_cast<int16_t *>(slotp + OFF_LIT_LO);
-    s.lit_cm = reinterpret_cast<int16_t *>(slotp + OFF_LIT_CM);
-    s.ctype_slabs = reinterpret_cast<int16_t *>(slotp + OFF_CTYPE);
-    s.dprior_slabs = reinterpret_cast<int16_t *>(slotp + OFF_DPRIOR);
-    s.misc = reinterpret_cast<int16_t *>(slotp + OFF_MISC);
-    s.lcm = slotp + OFF_LCM; s.mix = slotp + OFF_MIX; s.dcm = slotp + OFF_DCM;
-    s.bitmaps = smem + group_in_block * SMEM_WORDS_PER_GROUP;
-    s.scratch = reinterpret_cast<uint8_t *>(s.bitmaps + 80);
+    St s;
+    s.slot = p.arena + (uint64_t)slot * SLOT_STRIDE;
+    s.c = reinterpret_cast<Cold *>(smem + group_in_block * SMEM_BYTES_PER_GROUP);
     s.tables = p.tables;
-    s.desired_context_mixing = 0; s.desired_prior_depth = 0; s.desired_force_stride = 9; s.desired_do_context_map = true;
-    s.have_desired_adapt = false;
+    s.state = S_IDLE;
+    s.c->desired_context_mixing = 0; s.c->desired_prior_depth = 0; s.c->desired_force_stride = 9; s.c->desired_do_context_map = true;
+    s.c->have_desired_adapt = false; s.c->desired_adapt0 = s.c->desired_adapt1 = s.c->desired_adapt2 = s.c->desired_adapt3 = 0;
+    s.c->in.cmds = nullptr; s.c->in.n_cmds = 0; s.c->in.pos = 0; s.c->in.pms = nullptr; s.c->in.lits = nullptr;
+    s.c->sidx = 0; s.out = nullptr; s.out_pos = 0; s.c->out_cap = 0; s.c->ring_len = 1024;
+    st_reset(s);
+    coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0; coder_init_dec(s.c->oth, nullptr, 0);
+    Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.sym = 0; nx.mix_hi = false;
+    store_default_cdfs(g, reinterpret_cast<int16_t *>(s.slot + OFF_MISC), (uint32_t)MISC_CDFS);   // incl. the dummy CDF
+    bool exhausted = false;
 
-    uint64_t tot_cmd = 0, tot_lit = 0;
     for (;;) {
-        uint32_t sidx = 0;
-        if (g.store0) sidx = atomicAdd(p.work_counter, 1u);
-        sidx = __shfl_sync(g.mask, sidx, 0, LPS);
-        if (sidx >= p.n_streams) break;
-        if (p.status[sidx] != ST_OK) { if (g.store0) p.out_len[sidx] = 0; continue; }   // framing / CRC failure
-        const uint8_t *in = p.in + p.in_off[sidx];
-        const uint32_t body_end = p.body_end[sidx];
-        s.out = p.out + p.out_off[sidx]; s.out_cap = p.out_cap[sidx]; s.out_pos = 0;
-        s.ring_len = 1u << in[5];
-        stream_reset(s, g);
-        coder_init_dec(s.cmd, in + 16, in + body_end, 0);
-        coder_init_dec(s.lit, in + 16, in + body_end, 1);
-        // DivansCodec::encode_or_decode_one_command (codec/mod.rs:652-1024) fused with
-        // DivansDecoderCodec::decode_process_output (codec/decoder.rs:230-419)
-        for (;;) {
-            int t = cmd_nibble<false>(s, g, s.misc + (MI_CC + (s.last_4_states >> 4)) * 16, 0, DV_SPEED_ROCKET);
-            if (s.cmd.in.underflow) { s.status = ST_NEED_INPUT; break; }
-            if (t == 0xf) break;
-            if (t == 1) {   // copy
-                s.last_4_states = (s.last_4_states >> 2) | 64;
-                uint32_t d = 0, nb = 0;
-                code_copy<false>(s, g, d, nb);
-                if (s.status != ST_OK) break;
-                obs_distance(s, d);
-                replay_copy(s, g, d, nb);
-            } else if (t == 2) {   // dict
-                s.last_4_states = (s.last_4_states >> 2) | 192;
-                uint32_t id = 0, sz = 0, tr = 0;
-                code_dict<false>(s, g, id, sz, tr);
-                if (s.status != ST_OK) break;
-                replay_dict(s, g, sz, id, tr);
-            } else if (t == 3) {   // literal
-                s.last_4_states = (s.last_4_states >> 2) | 128;
-                uint32_t len = 0, he = 0;
-                code_literal_len<false>(s, g, len, he);
-                if (s.cmd.in.underflow) { s.status = ST_NEED_INPUT; break; }
-                if ((uint64_t)len > s.out_cap - s.out_pos) { s.status = ST_NEED_OUTPUT; break; }
-                ensure_literal_slabs(s, g);
-                if (s.mixing_trait) code_literal_bytes<false, true>(s, g, nullptr, len);
-                else code_literal_bytes<false, false>(s, g, nullptr, len);
-            } else if (t == 4) {   // literal block switch
-                uint32_t bt = code_btype<false>(s, g, 0, 0);
-                int stride = cmd_nibble<false>(s, g, s.misc + (MI_BTYPE + BT_STRIDE) * 16, 0, DV_SPEED_SLOW);
-                (void)stride;
-                obs_btype(s, 0, bt);
-                s.btype_last = bt;
-            } else if (t == 5) {
-                uint32_t bt = code_btype<false>(s, g, 1, 0); obs_btype(s, 1, bt);
-            } else if (t == 6) {
-                uint32_t bt = code_btype<false>(s, g, 2, 0); obs_btype(s, 2, bt);
-            } else if (t == 7) {
-                code_predmode<false>(s, g, nullptr);
-            } else { s.status = ST_FAIL; }   // CommandCodeOutOfBounds
-            if (s.status != ST_OK) break;
-            if (s.cmd.in.underflow || s.lit.in.underflow) { s.status = ST_NEED_INPUT; break; }
+        __syncwarp();
+        // ---- fetch work for idle groups (converged; the broadcast shuffle is executed by every lane) ----
+        const bool want = (s.state == S_IDLE) && !exhausted;
+        if (__any_sync(FULL, want)) {
+            uint32_t v = 0;
+            if (want && g.store0) v = atomicAdd(p.work_counter, 1u);
+            v = __shfl_sync(FULL, v, 0, LPS);
+            if (want) {
+                if (v >= p.n_streams) exhausted = true;
+                else if (p.status[v] != ST_OK) { if (g.store0) p.out_len[v] = 0; }   // framing / CRC failure: stay idle, fetch again
+                else {
+                    const uint8_t *in = p.in + p.in_off[v];
+                    const uint32_t pay0 = p.frame[4 * v + 1], pay1 = p.frame[4 * v + 2];
+                    const uint8_t *pl = p.payload + 16ull * p.frame[4 * v + 3];
+                    s.c->sidx = v;
+                    s.out = p.out + p.out_off[v];
+                    uint64_t cap = p.out_cap[v];
+                    s.c->out_cap = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap; s.out_pos = 0;
+                    s.c->ring_len = 1u << in[5];
+                    reset_slot(g, s.slot, s.c->bitmaps);
+                    st_reset(s);
+                    coder_init_dec(s.cur, reinterpret_cast<const uint32_t *>(pl), pay0 >> 2);   // command stream (CMD_CODER, codec/interface.rs:49)
+                    coder_init_dec(s.c->oth, reinterpret_cast<const uint32_t *>(pl + (((uint64_t)pay0 + 15) & ~15ull)), pay1 >> 2);   // literal stream (LIT_CODER, :50)
+                    enter_cmd_type<false>(s, nx);
+                }
+            }
+            if (__all_sync(FULL, exhausted && s.state == S_IDLE)) break;
+            __syncwarp();
         }
-        tot_cmd += s.cmd.n_syms; tot_lit += s.lit.n_syms;
-        if (g.store0) { p.out_len[sidx] = s.out_pos; p.status[sidx] = s.status; }
-    }
-    if (p.nibble_counts && g.store0) {
-        atomicAdd((unsigned long long *)&p.nibble_counts[0], (unsigned long long)tot_cmd);
-        atomicAdd((unsigned long long *)&p.nibble_counts[1], (unsigned long long)tot_lit);
+        // ---- one nibble per group ----
+        const bool busy = s.state != S_IDLE;
+        int sym = nibble_core<false, LPS>(s, nx, g, writer);
+        // ---- per-group scalar state machines (divergent) ----
+        if (busy) {
+            if (s.cur.underflow) s.status = ST_NEED_INPUT;
+            else transition<false>(s, nx, g, sym);
+            if (s.status != ST_OK || s.state == S_IDLE) {
+                if (s.status == ST_OK && s.c->oth.underflow) s.status = ST_NEED_INPUT;
+                if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
+                s.state = S_IDLE; s.status = ST_OK;
+                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE;
+                coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0;
+            }
+        }
     }
 }
 
 #if DV_LPS == 32
-void launch_frame(const FrameParams &p, cudaStream_t st) {
+void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st) {
     uint32_t blocks = (p.n_streams + 127) / 128;
     frame_kernel<<<blocks, 128, 0, st>>>(p);
+    payload_scan_kernel<<<1, 1024, 0, st>>>(p.frame, p.n_streams);
+    demux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p, payload);
 }
 // each translation unit has its own copy of the __constant__ LUT: upload to both
 cudaError_t upload_ctx_lut32(const uint8_t *host2048) { return cudaMemcpyToSymbol(c_ctx_lut, host2048, 2048); }
@@ -197,22 +309,22 @@ cudaError_t upload_ctx_lut16(const uint8_t *host2048) { return cudaMemcpyToSymbo
 #endif
 #if DV_LPS == 32
 void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
-    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_WORDS_PER_GROUP * 4;
+    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_BYTES_PER_GROUP;
     decode_kernel<32><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
 }
 int decode_max_blocks_per_sm32() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<32>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_WORDS_PER_GROUP * 4);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<32>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
 #else
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
-    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_WORDS_PER_GROUP * 4;
+    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP;
     decode_kernel<16><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
 }
 int decode_max_blocks_per_sm16() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_WORDS_PER_GROUP * 4);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
 #endif

@@ -23,89 +23,41 @@ __constant__ uint8_t c_ctx_lut[2048];   // mode*512 + {lut0[256], lut1[256]}   (
 struct Speed2 { int inc, lim; };
 
 // ---------------------------------------------------------------------------------------------------------------
-// input cursor: walks the mux records of ONE of the two interleaved byte streams in place (mux.rs:384-444), so the
-// raw .divans bytes are consumed straight from HBM -- no host-side demux pass.
-// ---------------------------------------------------------------------------------------------------------------
-struct InCursor {
-    const uint8_t *p;      // next payload byte of the current record
-    const uint8_t *nxt;    // first byte after the current record (= next record header)
-    const uint8_t *end;    // EOF marker position
-    uint32_t rem;          // payload bytes left in the current record
-    uint32_t sid;
-    uint32_t underflow;
-};
-
-__device__ __forceinline__ void cur_next_record(InCursor &c) {
-    while (true) {
-        if (c.nxt >= c.end) { c.underflow = 1; c.rem = 0; return; }
-        uint32_t b = __ldg(c.nxt);
-        uint32_t len, hdr;
-        if (b < 16) { len = ((uint32_t)__ldg(c.nxt + 1) | ((uint32_t)__ldg(c.nxt + 2) << 8)) + 1; hdr = 3; }
-        else { len = 1024u << ((b >> 4) << 1); hdr = 1; }
-        if ((b & 1) == c.sid) { c.p = c.nxt + hdr; c.rem = len; c.nxt = c.p + len; return; }
-        c.nxt += hdr + len;
-    }
-}
-__device__ __forceinline__ uint32_t cur_byte(InCursor &c) {
-    while (c.rem == 0) { if (c.underflow) return 0; cur_next_record(c); if (c.underflow) return 0; }
-    uint32_t v = __ldg(c.p); c.p++; c.rem--; return v;
-}
-__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p) {
-    // two aligned words + funnel shift; reads at most 3 bytes past p+4, always inside the stream (the 11 bytes of EOF
-    // marker + trailer follow every record)
-    const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-    uint32_t lo = __ldg(q), hi = __ldg(q + 1);
-    return __funnelshift_r(lo, hi, ((uint32_t)reinterpret_cast<uintptr_t>(p) & 3u) * 8u);
-}
-__device__ __forceinline__ uint32_t cur_u32_slow(InCursor &c) {
-    uint32_t v = cur_byte(c); v |= cur_byte(c) << 8; v |= cur_byte(c) << 16; v |= cur_byte(c) << 24;
-    return v;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// rANS coder state (src/ans.rs:142-148 decoder; :254-301 encoder records (start,freq))
+// rANS coder state (src/ans.rs:142-148 decoder; :254-301 encoder records (start,freq)).
+// The decoder reads its byte stream as aligned 32-bit words from a CONTIGUOUS payload: the mux records of the two
+// interleaved streams (mux.rs:384-444) are compacted by dv::demux_kernel before the stream kernel runs.
 // ---------------------------------------------------------------------------------------------------------------
 struct Coder {
     uint64_t a, b;
-    uint32_t sym_count, need_a, need_b;
-    InCursor in;
-    // encoder
-    uint32_t *sf;          // (start | freq<<16) log for this coder, whole stream
-    uint32_t n_sf;
-    uint32_t n_syms;
+    const uint32_t *p;     // DEC: next payload word.  ENC: base of this coder's (start | freq<<16) log
+    uint32_t left;         // DEC: payload words left. ENC: symbols logged so far
+    uint32_t sym_count, need_a, need_b, underflow;
 };
 
-__device__ __forceinline__ void coder_init_dec(Coder &k, const uint8_t *body, const uint8_t *end, uint32_t sid) {
-    k.a = k.b = 0; k.sym_count = 0; k.need_a = 8; k.need_b = 0;   // ans.rs:150-162
-    k.in.p = body; k.in.nxt = body; k.in.end = end; k.in.rem = 0; k.in.sid = sid; k.in.underflow = 0;
-    k.sf = nullptr; k.n_sf = 0; k.n_syms = 0;
+__device__ __forceinline__ void coder_init_dec(Coder &k, const uint32_t *payload, uint32_t n_words) {
+    k.a = k.b = 0; k.sym_count = 0; k.need_a = 8; k.need_b = 0; k.underflow = 0;   // ans.rs:150-162
+    k.p = payload; k.left = n_words;
 }
-// rare paths, by value so that the caller's Coder stays in registers: a word that straddles two mux records, and the
-// 16-byte (re)initialisation at stream start / every 65536 symbols (ans.rs:173-189)
-static __device__ __noinline__ Coder coder_fill_slow(Coder k) {
+__device__ __forceinline__ void coder_init_enc(Coder &k, uint32_t *log) {
+    k.a = k.b = 0; k.sym_count = 0; k.need_a = 0; k.need_b = 0; k.underflow = 0;
+    k.p = log; k.left = 0;
+}
+__device__ __forceinline__ void coder_fill(Coder &k) {
+    // ans.rs:428-442 (push_data) and :173-189 (16-byte (re)initialisation at stream start / every 65536 symbols)
+    if (k.need_a == 0) return;
     if (k.need_a == 1) {
-        uint32_t w = cur_u32_slow(k.in);
-        k.a = (k.a << 32) | (uint64_t)w;
+        if (k.left >= 1) { uint32_t w = __ldg(k.p); k.p += 1; k.left -= 1; k.a = (k.a << 32) | (uint64_t)w; }
+        else { k.underflow = 1; k.a <<= 32; }
     } else {
-        uint32_t w0 = cur_u32_slow(k.in), w1 = cur_u32_slow(k.in), w2 = cur_u32_slow(k.in), w3 = cur_u32_slow(k.in);
-        k.a = (uint64_t)w0 | ((uint64_t)w1 << 32);
-        k.b = (uint64_t)w2 | ((uint64_t)w3 << 32);
+        if (k.left >= 4) {
+            uint4 w = make_uint4(__ldg(k.p), __ldg(k.p + 1), __ldg(k.p + 2), __ldg(k.p + 3));
+            k.p += 4; k.left -= 4;
+            k.a = (uint64_t)w.x | ((uint64_t)w.y << 32);
+            k.b = (uint64_t)w.z | ((uint64_t)w.w << 32);
+        } else { k.underflow = 1; k.a = k.b = 0; k.left = 0; }
         k.sym_count = 0;
     }
     k.need_a = 0;
-    return k;
-}
-__device__ __forceinline__ void coder_fill(Coder &k) {
-    // ans.rs:428-442 (push_data)
-    if (k.need_a == 0) return;
-    if (k.need_a == 1 && k.in.rem >= 4) {
-        uint32_t w = ldg_u32_unaligned(k.in.p);
-        k.in.p += 4; k.in.rem -= 4;
-        k.a = (k.a << 32) | (uint64_t)w;
-        k.need_a = 0;
-        return;
-    }
-    k = coder_fill_slow(k);
 }
 __device__ __forceinline__ void coder_advance(Coder &k, int start, int freq) {
     // ans.rs:230-244
@@ -114,7 +66,6 @@ __device__ __forceinline__ void coder_advance(Coder &k, int start, int freq) {
     k.sym_count = (k.sym_count + 1) & 0xffff;
     k.need_b = (x < (1ull << 31)) ? 1u : 0u;
     k.a = k.b; k.b = x;
-    k.n_syms++;
 }
 
 // exact floor((c<<15)/max): the reference divides through a reciprocal LUT that is asserted equal to integer
@@ -124,7 +75,9 @@ __device__ __forceinline__ int cdf_div(int c, int maxv) {
     uint32_t d = (uint32_t)maxv & 0xffffu;
     uint32_t n = (uint32_t)(c << 15);
     if (d == 0) return (int)(n >> 1);           // RECIPROCAL[0] = (0,0) quirk (div_lut.rs)
-    float q = __uint2float_rz(n) * __fdividef(1.0f, __uint2float_rz(d));   // rcp.approx: 1 ulp, fixed up below
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rz(d)));   // 1 ulp, fixed up below
+    float q = __uint2float_rz(n) * rc;
     uint32_t qi = __float2uint_rz(q);
     int32_t r = (int32_t)(n - qi * d);
     if (r < 0) { qi--; r += (int32_t)d; }
@@ -141,35 +94,6 @@ struct Grp {
     bool lane0;        // l16 == 0 (scalar work; true on lane 16 too when the upper half mirrors)
     bool store0;       // the single lane that performs scalar stores for the group
 };
-
-// Code one nibble against the CDF whose element l16 is `c` (max = maxv).  Returns the symbol; start/freq out.
-template <bool ENC>
-__device__ __forceinline__ int code_cdf(Coder &k, const Grp g, int c, int maxv, int sym_in, int &start, int &freq) {
-    int sym;
-    if (!ENC) {
-        coder_fill(k);
-        int off = (int)(k.a & 0x7fff);
-        int r = (int)(short)((off * maxv) >> 15);                       // probability/interface.rs:140
-        bool pred = (g.l16 == 15) || (r < c);
-        unsigned bal = __ballot_sync(g.mask, pred);
-        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
-    } else {
-        sym = sym_in;
-    }
-    int cum = cdf_div(c, maxv);
-    int hi = __shfl_sync(g.mask, cum, sym, 16);
-    int lo = __shfl_sync(g.mask, cum, (sym - 1) & 15, 16);
-    if (sym == 0) lo = 0;
-    start = (int)(short)(lo + 1);                                       // "major hax", probability/interface.rs:103-104
-    freq = (int)(short)(hi - lo - 1);
-    if (!ENC) {
-        coder_advance(k, start, freq);
-    } else {
-        if (g.store0) k.sf[k.n_sf] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16);   // ans.rs:289-296
-        k.n_sf++; k.n_syms++;
-    }
-    return sym;
-}
 
 // freq only (for the mixing weights: codec/literal.rs:236-239)
 __device__ __forceinline__ int cdf_freq(const Grp g, int c, int maxv, int sym) {
@@ -189,19 +113,6 @@ __device__ __forceinline__ int cdf_blend(const Grp g, int c, int maxv, int sym, 
         c2 = (int)(short)(t - (t >> 2));
     }
     return c2;
-}
-
-// code a nibble against a prior stored in HBM and adapt it
-template <bool ENC>
-__device__ __forceinline__ int code_prior(Coder &k, const Grp g, int16_t *cdf, int sym_in, int inc, int lim) {
-    int c = cdf[g.l16];
-    int maxv = cdf[15];
-    int start, freq;
-    int sym = code_cdf<ENC>(k, g, c, maxv, sym_in, start, freq);
-    int c2 = cdf_blend(g, c, maxv, sym, inc, lim);
-    if (g.writer) cdf[g.l16] = (int16_t)c2;
-    __syncwarp(g.mask);
-    return sym;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

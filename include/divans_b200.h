@@ -123,11 +123,12 @@ DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const
                                            const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                            const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags);
 /* Same, all pointers are DEVICE pointers (inputs already resident in HBM, outputs left in HBM).
- * `cuda_stream` is a cudaStream_t (NULL = the context's own stream).  Asynchronous: returns after enqueueing. */
+ * `in_total_bytes` = size of the d_in blob (upper bound of sum(in_len)); `cuda_stream` is a cudaStream_t (NULL = the
+ * context's own stream).  Asynchronous: returns after enqueueing. */
 DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                              const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
                                              const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
-                                             uint32_t flags, void *cuda_stream);
+                                             uint64_t in_total_bytes, uint32_t flags, void *cuda_stream);
 DivansResult divans_b200_synchronize(divans_b200_ctx *ctx);
 
 /* Encoder options (subset of the reference's DivansCompressorOptions, src/interface.rs:444-484, that affects the
