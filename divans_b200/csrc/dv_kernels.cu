@@ -213,6 +213,30 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
     return sym;
 }
 
+// Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
+// (high nibble, low nibble, context of the next byte) back to back without going through the state-machine dispatch.
+// This is code_nibble_array (codec/literal.rs:261-394) for two streams at once.
+template <bool ENC, int LPS>
+__device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const bool writer) {
+    uint32_t n = s.lit_left;
+    if (LPS == 16) n = min(n, __shfl_xor_sync(FULL, n, 16));
+    for (uint32_t i = 0; i < n; i++) {
+        __syncwarp();
+        int h = nibble_core<ENC, LPS>(s, nx, g, writer);
+        s.lit_h = (uint32_t)h;
+        enter_lit_nibble<ENC, false>(s, nx);
+        __syncwarp();
+        int l = nibble_core<ENC, LPS>(s, nx, g, writer);
+        uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+        s.l8 = (s.l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
+        if (g.store0) s.out[s.out_pos] = (uint8_t)cur;
+        s.out_pos++;
+        s.lit_left--;
+        lit_context(s);
+        enter_lit_nibble<ENC, true>(s, nx);
+    }
+}
+
 template <int LPS>
 __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -275,6 +299,18 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodePara
             __syncwarp();
         }
         // ---- one nibble per group ----
+        if (__all_sync(FULL, s.state == S_LIT_HI)) {
+            literal_fast<false, LPS>(s, nx, g, writer);
+            if (s.cur.underflow) s.status = ST_NEED_INPUT;
+            if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); enter_cmd_type<false>(s, nx); }
+            if (s.status != ST_OK) {
+                if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
+                s.state = S_IDLE; s.status = ST_OK;
+                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE;
+                coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0;
+            }
+            continue;
+        }
         const bool busy = s.state != S_IDLE;
         int sym = nibble_core<false, LPS>(s, nx, g, writer);
         // ---- per-group scalar state machines (divergent) ----
