@@ -213,13 +213,81 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
     return sym;
 }
 
+// Plain (non-mixing) nibble step on explicit operands: the body of the literal fast path.
+template <bool ENC>
+__device__ __forceinline__ int lit_step(Coder &k, const G2 g, const bool writer, int16_t *cdf, const int inc, const int lim, const int sym_in) {
+    const int c = cdf[g.l16], maxv = cdf[15];
+    int sym;
+    if (!ENC) {
+        coder_fill(k);
+        int off = (int)(k.a & 0x7fff);
+        int r = (int)(short)((off * maxv) >> 15);
+        bool pred = (g.l16 == 15) || (r < c);
+        unsigned bal = __ballot_sync(FULL, pred);
+        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
+    } else sym = sym_in;
+    int cum = cdf_div(c, maxv);
+    int hi = __shfl_sync(FULL, cum, sym, 16);
+    int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
+    if (sym == 0) lo = 0;
+    int start = (int)(short)(lo + 1), freq = (int)(short)(hi - lo - 1);
+    if (!ENC) coder_advance(k, start, freq);
+    else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
+    int c2 = (int)(short)(c + ((g.l16 >= sym) ? inc : 0));
+    if ((int)(short)(maxv + inc) >= lim) { int t = (int)(short)(c2 + g.l16 + 1); c2 = (int)(short)(t - (t >> 2)); }
+    if (writer) cdf[g.l16] = (int16_t)c2;
+    return sym;
+}
+
 // Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
 // (high nibble, low nibble, context of the next byte) back to back without going through the state-machine dispatch.
-// This is code_nibble_array (codec/literal.rs:261-394) for two streams at once.
+// This is code_nibble_array (codec/literal.rs:261-394) for two streams at once.  The common case -- no dynamic context
+// mixing and one mixing-mask value for the whole map -- gets a loop with every selector hoisted out.
 template <bool ENC, int LPS>
 __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const bool writer) {
     uint32_t n = s.lit_left;
     if (LPS == 16) n = min(n, __shfl_xor_sync(FULL, n, 16));
+    const bool simple = __all_sync(FULL, !s.mixing_trait && s.lit_cfg >= 0);
+    if (simple) {
+        const int cfg = s.lit_cfg;
+        const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;
+        const uint32_t sh = (uint32_t)(cfg >> 2) & 63u, which = (uint32_t)cfg & 3u;
+        const bool ro = (cfg & 0x800) != 0;
+        const int inc = ro ? 0 : (int)(short)(s.ad_stride & 0xffff), lim = ro ? 0x7fff : (s.ad_stride >> 16);
+        int16_t *const hi_base = A_lit(s, true) + (size_t)which * 256 * 256 * 16;
+        int16_t *const lo_base = A_lit(s, false) + (size_t)which * 256 * 256 * 16;
+        int16_t *const flat = A_misc(s, MI_FLAT);
+        const uint8_t *const lcm = A_lcm(s) + (s.btype_last << 6);
+        const uint8_t *const lut = s.tables + TB_CTX + 512 * s.pred_mode;
+        const uint32_t pm = s.pred_mode;
+        const uint8_t *src = ENC ? s.c->in.lits + s.c->e0 + (s.c->e1 - s.lit_left) : nullptr;
+        unsigned long long l8 = s.l8;
+        uint32_t ctx = s.lit_ctx;
+        uint8_t *dst = s.out + s.out_pos;
+        Coder k = s.cur;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
+            const uint32_t byte_in = ENC ? src[i] : 0u;
+            __syncwarp();
+            int16_t *ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssb & mm & (~o1 & 0xffu)))) * 16;
+            const int h = lit_step<ENC>(k, g, writer, ph, inc, lim, (int)(byte_in >> 4));
+            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
+            __syncwarp();
+            int16_t *pl = ro ? flat : lo_base + ((size_t)(ic * 256 + ib)) * 16;
+            const int l = lit_step<ENC>(k, g, writer, pl, inc, lim, (int)(byte_in & 0xf));
+            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
+            if (g.store0) dst[i] = (uint8_t)cur;
+            uint32_t sel;                                         // get_prev_word_context, codec/literal.rs:87-117
+            if (pm == 0) sel = cur & 0x3f;
+            else if (pm == 1) sel = cur >> 2;
+            else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+            ctx = lcm[sel];
+        }
+        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
+        enter_lit_nibble<ENC, true>(s, nx);
+        return;
+    }
     for (uint32_t i = 0; i < n; i++) {
         __syncwarp();
         int h = nibble_core<ENC, LPS>(s, nx, g, writer);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void coder_advance(Coder &k, int start, int freq) {
     // ans.rs:230-244
     k.need_a = k.need_b | ((k.sym_count == NUM_SYMBOLS_BEFORE_FLUSH - 1) ? 8u : 0u);
     uint64_t x = (uint64_t)(int64_t)freq * (k.a >> 15) + (k.a & 0x7fff) - (uint64_t)(int64_t)start;
-    k.sym_count = (k.sym_count + 1) & 0xffff;
+    k.sym_count = k.sym_count + 1;   // reset by the 16-byte re-initialisation that always follows symbol 65535
     k.need_b = (x < (1ull << 31)) ? 1u : 0u;
     k.a = k.b; k.b = x;
 }
@@ -74,7 +74,6 @@ __device__ __forceinline__ void coder_advance(Coder &k, int start, int freq) {
 __device__ __forceinline__ int cdf_div(int c, int maxv) {
     uint32_t d = (uint32_t)maxv & 0xffffu;
     uint32_t n = (uint32_t)(c << 15);
-    if (d == 0) return (int)(n >> 1);           // RECIPROCAL[0] = (0,0) quirk (div_lut.rs)
     float rc;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rz(d)));   // 1 ulp, fixed up below
     float q = __uint2float_rz(n) * rc;
