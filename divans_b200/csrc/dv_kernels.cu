@@ -213,30 +213,34 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
     return sym;
 }
 
-// Plain (non-mixing) nibble step on explicit operands: the body of the literal fast path.
+// Plain (non-mixing) nibble step split in three phases so that the literal fast path can software-pipeline it:
+//   lit_load   issue the two loads of the prior (element l16 and the maximum)
+//   lit_search refill the rANS state if needed and find the symbol (ballot)       -- on the critical path
+//   lit_finish exact start/freq, rANS state update, adaptive blend, store         -- off the critical path
+struct CdfRegs { int c, maxv; };
+__device__ __forceinline__ CdfRegs lit_load(const G2 g, const int16_t *cdf) { CdfRegs r; r.c = cdf[g.l16]; r.maxv = cdf[15]; return r; }
 template <bool ENC>
-__device__ __forceinline__ int lit_step(Coder &k, const G2 g, const bool writer, int16_t *cdf, const int inc, const int lim, const int sym_in) {
-    const int c = cdf[g.l16], maxv = cdf[15];
-    int sym;
-    if (!ENC) {
-        coder_fill(k);
-        int off = (int)(k.a & 0x7fff);
-        int r = (int)(short)((off * maxv) >> 15);
-        bool pred = (g.l16 == 15) || (r < c);
-        unsigned bal = __ballot_sync(FULL, pred);
-        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
-    } else sym = sym_in;
-    int cum = cdf_div(c, maxv);
+__device__ __forceinline__ int lit_search(Coder &k, const G2 g, const CdfRegs r, const int sym_in) {
+    if (ENC) return sym_in;
+    coder_fill(k);
+    int off = (int)(k.a & 0x7fff);
+    int rr = (int)(short)((off * r.maxv) >> 15);                      // probability/interface.rs:140
+    bool pred = (g.l16 == 15) || (rr < r.c);
+    unsigned bal = __ballot_sync(FULL, pred);
+    return __ffs((bal >> g.shift) & 0xffffu) - 1;
+}
+template <bool ENC>
+__device__ __forceinline__ void lit_finish(Coder &k, const G2 g, const bool writer, int16_t *cdf, const CdfRegs r, const int sym, const int inc, const int lim) {
+    int cum = cdf_div(r.c, r.maxv);
     int hi = __shfl_sync(FULL, cum, sym, 16);
     int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
     if (sym == 0) lo = 0;
-    int start = (int)(short)(lo + 1), freq = (int)(short)(hi - lo - 1);
+    int start = (int)(short)(lo + 1), freq = (int)(short)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
     if (!ENC) coder_advance(k, start, freq);
     else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
-    int c2 = (int)(short)(c + ((g.l16 >= sym) ? inc : 0));
-    if ((int)(short)(maxv + inc) >= lim) { int t = (int)(short)(c2 + g.l16 + 1); c2 = (int)(short)(t - (t >> 2)); }
+    int c2 = (int)(short)(r.c + ((g.l16 >= sym) ? inc : 0));
+    if ((int)(short)(r.maxv + inc) >= lim) { int t = (int)(short)(c2 + g.l16 + 1); c2 = (int)(short)(t - (t >> 2)); }
     if (writer) cdf[g.l16] = (int16_t)c2;
-    return sym;
 }
 
 // Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
@@ -265,16 +269,27 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         uint32_t ctx = s.lit_ctx;
         uint8_t *dst = s.out + s.out_pos;
         Coder k = s.cur;
+        // Software pipeline (the loads of the NEXT prior are issued before the bookkeeping of the CURRENT nibble):
+        //   search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo)
+        // The high and low tables never alias, so the early loads cannot overtake a store to the same CDF; the
+        // __syncwarp()s order each store against the next load of the same table across lanes.
+        int16_t *ph; int16_t *pl;
+        {
+            const uint32_t ssb0 = (uint32_t)(l8 >> sh) & 0xffu;
+            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssb0 & mm & (~o1 & 0xffu)))) * 16;
+        }
+        __syncwarp();
+        CdfRegs rh = lit_load(g, ph);
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
             const uint32_t byte_in = ENC ? src[i] : 0u;
-            __syncwarp();
-            int16_t *ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssb & mm & (~o1 & 0xffu)))) * 16;
-            const int h = lit_step<ENC>(k, g, writer, ph, inc, lim, (int)(byte_in >> 4));
+            const int h = lit_search<ENC>(k, g, rh, (int)(byte_in >> 4));
             const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
+            pl = ro ? flat : lo_base + ((size_t)(ic * 256 + ib)) * 16;
             __syncwarp();
-            int16_t *pl = ro ? flat : lo_base + ((size_t)(ic * 256 + ib)) * 16;
-            const int l = lit_step<ENC>(k, g, writer, pl, inc, lim, (int)(byte_in & 0xf));
+            const CdfRegs rl = lit_load(g, pl);
+            lit_finish<ENC>(k, g, writer, ph, rh, h, inc, lim);
+            const int l = lit_search<ENC>(k, g, rl, (int)(byte_in & 0xf));
             const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
             l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
             if (g.store0) dst[i] = (uint8_t)cur;
@@ -283,6 +298,11 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
             else if (pm == 1) sel = cur >> 2;
             else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
             ctx = lcm[sel];
+            const uint32_t ssbn = (uint32_t)(l8 >> sh) & 0xffu;
+            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssbn & mm & (~o1 & 0xffu)))) * 16;
+            __syncwarp();
+            rh = lit_load(g, ph);                                 // speculative on the last byte: a valid, initialised slab
+            lit_finish<ENC>(k, g, writer, pl, rl, l, inc, lim);
         }
         s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
         enter_lit_nibble<ENC, true>(s, nx);
