@@ -36,7 +36,7 @@ BATCH_SYMBOLS = [
     "divans_b200_create", "divans_b200_destroy", "divans_b200_last_error", "divans_b200_launch_count",
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
-    "divans_b200_encode_cmds_batch_host",
+    "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device",
 ]
 
 
@@ -94,6 +94,8 @@ def load_library():
     L.divans_b200_encode_batch_host.restype = ctypes.c_uint8
     L.divans_b200_encode_cmds_batch_host.argtypes = batch + [ctypes.POINTER(EncodeOptions)]
     L.divans_b200_encode_cmds_batch_host.restype = ctypes.c_uint8
+    L.divans_b200_encode_batch_device.argtypes = [vp, sz, vp, vp, vp, ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.POINTER(EncodeOptions), vp]
+    L.divans_b200_encode_batch_device.restype = ctypes.c_uint8
     # reference FFI
     L.divans_new_decompressor.restype = vp
     L.divans_new_serial_decompressor.restype = vp
@@ -229,6 +231,15 @@ class Engine:
         if rc != DIVANS_SUCCESS:
             raise DivansError("encode_batch_host: " + self._err())
         return out_len, status
+
+    def encode_batch_device(self, n, d_in, d_in_off, d_in_len, max_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, opts=None,
+                            stream=None):
+        """All arguments are raw device pointers (ints).  Asynchronous on ``stream``."""
+        o = opts or encode_options()
+        rc = self._L.divans_b200_encode_batch_device(self._h, n, d_in, d_in_off, d_in_len, int(max_in_len), d_out, d_out_off, d_out_cap,
+                                                     d_out_len, d_status, ctypes.byref(o), stream)
+        if rc != DIVANS_SUCCESS:
+            raise DivansError("encode_batch_device: " + self._err())
 
     def encode(self, raws, opts=None, cmds=False):
         """Convenience: list of raw byte strings (or DVCL command-list blobs with cmds=True) -> list of .divans bytes."""

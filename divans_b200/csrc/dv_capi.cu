@@ -44,7 +44,12 @@ struct divans_b200_ctx {
     uint8_t *d_in = nullptr; size_t d_in_cap = 0;
     uint8_t *d_out = nullptr; size_t d_out_cap = 0;
     uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;   // in_off,in_len,out_off,out_cap,out_len (+status)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;   // ev0 | frame kernel | evm | decode kernel | ev1
+    uint32_t *d_sf = nullptr; size_t sf_cap = 0;               // encoder: symbol logs
+    uint8_t *d_replay = nullptr; size_t replay_cap = 0;
+    uint32_t *d_enc_scratch = nullptr; size_t enc_scratch_cap = 0;
+    uint8_t *d_pm_internal = nullptr; std::vector<uint8_t> h_pm;
+    bool main_end_is_evm1 = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, evm1 = nullptr;   // ev0 | frame kernel | evm | decode kernel | ev1
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
     std::string err;
@@ -88,7 +93,7 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = ck(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               ck(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate") &&
-              ck(ctx, cudaEventCreate(&ctx->evm), "cudaEventCreate") &&
+              ck(ctx, cudaEventCreate(&ctx->evm), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->evm1), "cudaEventCreate") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_tables, TB_TOTAL), "cudaMalloc(tables)") &&
               ck(ctx, cudaMemcpy(ctx->d_tables, dv_tables_blob, TB_TOTAL, cudaMemcpyHostToDevice), "cudaMemcpy(tables)") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_counter, 64), "cudaMalloc(counter)") &&
@@ -119,6 +124,8 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evm) cudaEventDestroy(ctx->evm);
+    if (ctx->evm1) cudaEventDestroy(ctx->evm1);
+    cudaFree(ctx->d_sf); cudaFree(ctx->d_replay); cudaFree(ctx->d_enc_scratch); cudaFree(ctx->d_pm_internal);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -133,7 +140,7 @@ extern "C" float divans_b200_last_kernel_ms(divans_b200_ctx *ctx) {
 extern "C" float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx) {
     if (!ctx) return 0.f;
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->evm, ctx->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->evm, ctx->main_end_is_evm1 ? ctx->evm1 : ctx->ev1) != cudaSuccess) return -1.f;
     return ms;
 }
 extern "C" DivansResult divans_b200_synchronize(divans_b200_ctx *ctx) {
@@ -182,6 +189,7 @@ extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, si
     if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
+    ctx->main_end_is_evm1 = false;
     ctx->launches += skip_decode ? 3 : 4;
     CK(cudaGetLastError());
     return DIVANS_SUCCESS;
@@ -235,19 +243,187 @@ extern "C" void divans_b200_encode_options_default(divans_b200_encode_options *o
     o->window_size = 22; o->dynamic_context_mixing = 0; o->prior_depth = 0; o->use_context_map = 1; o->force_stride = 9;
     o->literal_pred_mode = 0; o->literal_mixing_value = 4;
 }
-extern "C" DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size_t, const uint8_t *, const uint64_t *, const uint64_t *,
-                                                      uint8_t *, const uint64_t *, const uint64_t *, uint64_t *, int32_t *,
-                                                      const divans_b200_encode_options *) {
-    if (ctx) ctx->err = "GPU encoder not built yet";
-    fprintf(stderr, "divans_b200: GPU encoder not implemented in this build\n");
-    return DIVANS_FAILURE;
+// ---- encoder ----
+static inline int pack_speed(const int16_t sp[2]) { return (int)((uint32_t)(uint16_t)sp[0] | ((uint32_t)(uint16_t)sp[1] << 16)); }
+
+// One launch set over n streams whose inputs/outputs already sit in HBM.  `cmd_cap`/`lit_cap`: log entries per stream,
+// `replay_stride`: bytes of replay window per resident slot.
+static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int raw_mode, const uint8_t *d_in, const uint64_t *d_in_off,
+                                           const uint64_t *d_in_len, uint32_t cmd_cap, uint32_t lit_cap, uint64_t replay_stride,
+                                           uint8_t *d_out, const uint64_t *d_out_off, const uint64_t *d_out_cap, uint64_t *d_out_len,
+                                           int32_t *d_status, const divans_b200_encode_options *o, cudaStream_t st) {
+    const uint32_t gpb = DECODE_BLOCK_THREADS / 16;
+    int per_sm = encode_max_blocks_per_sm(); if (per_sm < 1) per_sm = 1;
+    uint32_t max_res = (uint32_t)ctx->sm_count * (uint32_t)per_sm * gpb;
+    if (ctx->max_resident < max_res) max_res = ctx->max_resident;
+    uint32_t resident = (uint32_t)(n < max_res ? n : max_res);
+    uint32_t blocks = (resident + gpb - 1) / gpb;
+    size_t slots = (size_t)blocks * gpb;
+    if (ensure_arena(ctx, slots) != DIVANS_SUCCESS) return DIVANS_FAILURE;
+    const uint32_t cmd_chunks = (cmd_cap + NUM_SYMBOLS_BEFORE_FLUSH - 1) / NUM_SYMBOLS_BEFORE_FLUSH;
+    const uint32_t lit_chunks = (lit_cap + NUM_SYMBOLS_BEFORE_FLUSH - 1) / NUM_SYMBOLS_BEFORE_FLUSH;
+    const uint32_t max_chunks = cmd_chunks + lit_chunks;
+    if (!grow(ctx, &ctx->d_sf, &ctx->sf_cap, n * ((size_t)cmd_cap + lit_cap))) return DIVANS_FAILURE;
+    if (!grow(ctx, &ctx->d_replay, &ctx->replay_cap, slots * (size_t)replay_stride)) return DIVANS_FAILURE;
+    // small per-stream scratch: counts [2n] | dummy [slots] | chunk_w [n*max_chunks] | chunk_state [16*n*max_chunks]
+    size_t words = 2 * n + slots + n * (size_t)max_chunks + 4 * n * (size_t)max_chunks + 16;
+    if (!grow(ctx, &ctx->d_enc_scratch, &ctx->enc_scratch_cap, words)) return DIVANS_FAILURE;
+    if (!ctx->d_pm_internal) CK(cudaMalloc((void **)&ctx->d_pm_internal, PM_RECORD_BYTES));
+    if (raw_mode) {
+        // raw_to_cmd/mod.rs:116-143: 64-entry identity literal map, 4 distance entries, one mixing value, speeds unset
+        std::vector<uint8_t> &pm = ctx->h_pm;
+        pm.assign(PM_RECORD_BYTES, 0);
+        pm[0] = (uint8_t)o->literal_pred_mode; pm[2] = 1;
+        pm[28] = 64; pm[30] = 4;
+        for (int i = 0; i < 64; i++) pm[32 + i] = (uint8_t)i;
+        for (int i = 0; i < 4; i++) pm[32 + 16384 + i] = (uint8_t)i;
+        memset(pm.data() + 32 + 16384 + 1024, o->literal_mixing_value, 8192);
+        CK(cudaMemcpyAsync(ctx->d_pm_internal, pm.data(), PM_RECORD_BYTES, cudaMemcpyHostToDevice, st));
+    }
+    EncodeParams ep;
+    ep.in = d_in; ep.in_off = d_in_off; ep.in_len = d_in_len; ep.raw_mode = raw_mode; ep.n_streams = (uint32_t)n;
+    ep.work_counter = ctx->d_counter; ep.arena = ctx->d_arena; ep.tables = ctx->d_tables; ep.pm_internal = ctx->d_pm_internal;
+    ep.sf = ctx->d_sf; ep.cmd_cap = cmd_cap; ep.lit_cap = lit_cap;
+    uint32_t *w = ctx->d_enc_scratch;
+    ep.sf_counts = w; w += 2 * n;
+    ep.sf_dummy = w; w += slots;
+    ep.chunk_w = w; w += n * (size_t)max_chunks;
+    w = reinterpret_cast<uint32_t *>(((uintptr_t)w + 15) & ~(uintptr_t)15);
+    ep.chunk_state = reinterpret_cast<uint8_t *>(w);
+    ep.replay = ctx->d_replay; ep.replay_stride = replay_stride;
+    ep.max_chunks = max_chunks; ep.cmd_chunks = cmd_chunks;
+    ep.out = d_out; ep.out_off = d_out_off; ep.out_cap = d_out_cap; ep.out_len = d_out_len; ep.status = d_status;
+    int window = o->window_size < 10 ? 10 : (o->window_size > 24 ? 24 : o->window_size);
+    ep.window_size = window; ep.dynamic_context_mixing = o->dynamic_context_mixing & 0xff; ep.prior_depth = o->prior_depth & 0xff;
+    ep.use_context_map = o->use_context_map; ep.force_stride = o->force_stride; ep.have_literal_adaptation = o->have_literal_adaptation;
+    for (int k = 0; k < 4; k++) ep.literal_adaptation[k] = pack_speed(o->literal_adaptation[k]);
+    CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(cudaEventRecord(ctx->evm, st));
+    launch_encode_model(ep, blocks, st);
+    CK(cudaEventRecord(ctx->evm1, st));
+    launch_encode_flush_mux(ep, st);
+    CK(cudaEventRecord(ctx->ev1, st));
+    ctx->main_end_is_evm1 = true;
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    return DIVANS_SUCCESS;
 }
-extern "C" DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t, const uint8_t *, const uint64_t *,
-                                                           const uint64_t *, uint8_t *, const uint64_t *, const uint64_t *, uint64_t *,
-                                                           int32_t *, const divans_b200_encode_options *) {
-    if (ctx) ctx->err = "GPU encoder not built yet";
-    fprintf(stderr, "divans_b200: GPU encoder not implemented in this build\n");
-    return DIVANS_FAILURE;
+
+static uint32_t raw_cmd_cap(uint64_t max_len, int window) { return (uint32_t)(32 * (2 + (max_len >> window)) + 62000 + 64); }
+
+extern "C" DivansResult divans_b200_encode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                                        const uint64_t *d_in_len, uint64_t max_in_len, uint8_t *d_out,
+                                                        const uint64_t *d_out_off, const uint64_t *d_out_cap, uint64_t *d_out_len,
+                                                        int32_t *d_status, const divans_b200_encode_options *opts, void *cuda_stream) {
+    if (!ctx || !opts) return DIVANS_FAILURE;
+    if (n == 0) return DIVANS_SUCCESS;
+    if (n > 0xffffffffull || max_in_len > 0x7fff0000ull) { ctx->err = "batch too large"; return DIVANS_FAILURE; }
+    CK(cudaSetDevice(ctx->device));
+    int window = opts->window_size < 10 ? 10 : (opts->window_size > 24 ? 24 : opts->window_size);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    return encode_device_internal(ctx, n, 1, d_in, d_in_off, d_in_len, raw_cmd_cap(max_in_len, window), (uint32_t)(2 * max_in_len + 16),
+                                  (max_in_len + 31) & ~15ull, d_out, d_out_off, d_out_cap, d_out_len, d_status, opts, st);
+}
+
+// host batch: marshal, split into sub-batches whose symbol logs fit in HBM, run, copy back
+static DivansResult encode_host_common(divans_b200_ctx *ctx, size_t n, int raw_mode, const uint8_t *in, const uint64_t *in_off,
+                                       const uint64_t *in_len, uint8_t *out, const uint64_t *out_off, const uint64_t *out_cap,
+                                       uint64_t *out_len, int32_t *status, const divans_b200_encode_options *opts) {
+    if (!ctx || !opts) return DIVANS_FAILURE;
+    if (n == 0) return DIVANS_SUCCESS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    const int window = opts->window_size < 10 ? 10 : (opts->window_size > 24 ? 24 : opts->window_size);
+    // per-stream requirements
+    std::vector<uint64_t> s_off(n), need_cmd(n), need_lit(n), need_replay(n);
+    std::vector<uint8_t> staged;   // command lists are re-based to 4-byte aligned offsets
+    uint64_t in_end = 0;
+    for (size_t i = 0; i < n; i++) {
+        status[i] = DIVANS_FAILURE; out_len[i] = 0;
+        if (raw_mode) {
+            if (in_len[i] > 0x7fff0000ull) { ctx->err = "stream too large"; return DIVANS_FAILURE; }
+            s_off[i] = in_off[i];
+            need_cmd[i] = raw_cmd_cap(in_len[i], window); need_lit[i] = 2 * in_len[i] + 16; need_replay[i] = (in_len[i] + 31) & ~15ull;
+            if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
+        } else {
+            const uint8_t *b = in + in_off[i];
+            uint32_t h[8] = {0};
+            if (in_len[i] >= 32) memcpy(h, b, 32);
+            uint64_t need = 32ull + 20ull * h[2] + (uint64_t)PM_RECORD_BYTES * h[3] + h[4];
+            uint64_t lit = 0, rep = 0;
+            if (in_len[i] >= 32 && h[0] == 0x4c435644u && h[1] == 1 && need <= in_len[i]) {
+                for (uint32_t c = 0; c < h[2]; c++) {
+                    uint32_t r[5]; memcpy(r, b + 32 + 20ull * c, 20);
+                    if (r[0] == 1) rep += r[2];
+                    else if (r[0] == 2) rep += 64;            // dictionary word + transform prefix/suffix
+                    else if (r[0] == 3) { lit += r[2]; rep += r[2]; }
+                }
+            }
+            if (lit > 0x7fff0000ull || rep > 0xfffffff0ull) { ctx->err = "stream too large"; return DIVANS_FAILURE; }
+            need_cmd[i] = 32ull * h[2] + 62000ull * h[3] + 64; need_lit[i] = 2 * lit + 16; need_replay[i] = (rep + 31) & ~15ull;
+            s_off[i] = (staged.size() + 3) & ~(size_t)3;
+            staged.resize(s_off[i] + in_len[i]);
+            if (in_len[i]) memcpy(staged.data() + s_off[i], b, in_len[i]);
+            in_end = staged.size();
+        }
+    }
+    const uint8_t *src = raw_mode ? in : staged.data();
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const uint64_t budget = (uint64_t)(free_b + ctx->sf_cap * 4) * 6 / 10;
+    if (!grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)in_end + 64)) return DIVANS_FAILURE;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_in, src, in_end, cudaMemcpyHostToDevice, st));
+    size_t i0 = 0;
+    while (i0 < n) {
+        // grow the sub-batch while its uniform-capacity logs fit
+        uint64_t mc = 0, ml = 0, mr = 0; size_t i1 = i0;
+        while (i1 < n) {
+            uint64_t c = need_cmd[i1] > mc ? need_cmd[i1] : mc, l = need_lit[i1] > ml ? need_lit[i1] : ml;
+            if (i1 > i0 && (c + l) * 4 * (uint64_t)(i1 - i0 + 1) > budget) break;
+            mc = c; ml = l; if (need_replay[i1] > mr) mr = need_replay[i1];
+            i1++;
+        }
+        if (mc > 0xffffffffull || ml > 0xffffffffull) { ctx->err = "stream too large"; return DIVANS_FAILURE; }
+        const size_t m = i1 - i0;
+        uint64_t out_lo = ~0ull, out_hi = 0;
+        for (size_t i = i0; i < i1; i++) { if (out_off[i] < out_lo) out_lo = out_off[i]; if (out_off[i] + out_cap[i] > out_hi) out_hi = out_off[i] + out_cap[i]; }
+        if (!grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)(out_hi - out_lo) + 64)) return DIVANS_FAILURE;
+        if (!grow(ctx, &ctx->d_meta, &ctx->d_meta_cap, m * 6)) return DIVANS_FAILURE;
+        std::vector<uint64_t> rel(m);
+        for (size_t i = 0; i < m; i++) rel[i] = out_off[i0 + i] - out_lo;
+        uint64_t *mm = ctx->d_meta;
+        CK(cudaMemcpyAsync(mm, s_off.data() + i0, m * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(mm + m, in_len + i0, m * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(mm + 2 * m, rel.data(), m * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(mm + 3 * m, out_cap + i0, m * 8, cudaMemcpyHostToDevice, st));
+        int32_t *d_status = reinterpret_cast<int32_t *>(mm + 5 * m);
+        DivansResult r = encode_device_internal(ctx, m, raw_mode, ctx->d_in, mm, mm + m, (uint32_t)mc, (uint32_t)ml, mr, ctx->d_out, mm + 2 * m,
+                                                mm + 3 * m, mm + 4 * m, d_status, opts, st);
+        if (r != DIVANS_SUCCESS) return r;
+        CK(cudaMemcpyAsync(out_len + i0, mm + 4 * m, m * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status + i0, d_status, m * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = i0; i < i1; i++) {
+            if (status[i] == DIVANS_SUCCESS && out_len[i]) CK(cudaMemcpyAsync(out + out_off[i], ctx->d_out + (out_off[i] - out_lo), out_len[i], cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        i0 = i1;
+    }
+    return DIVANS_SUCCESS;
+}
+extern "C" DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                                      const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                                      const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
+                                                      const divans_b200_encode_options *opts) {
+    return encode_host_common(ctx, n, 1, in, in_off, in_len, out, out_off, out_cap, out_len, status, opts);
+}
+extern "C" DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *blobs, const uint64_t *blob_off,
+                                                           const uint64_t *blob_len, uint8_t *out, const uint64_t *out_off,
+                                                           const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
+                                                           const divans_b200_encode_options *opts) {
+    return encode_host_common(ctx, n, 0, blobs, blob_off, blob_len, out, out_off, out_cap, out_len, status, opts);
 }
 
 // =================================================================================================================

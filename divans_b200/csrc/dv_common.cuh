@@ -97,6 +97,33 @@ struct FrameParams {
     uint32_t flags;
 };
 
+// Encoder (model pass -> reverse rANS pass -> mux/CRC pass).  Every stream owns `cmd_cap + lit_cap` u32 log entries
+// (start | freq << 16, ans.rs:289-301): the command coder's log first, then the literal coder's.
+struct EncodeParams {
+    const uint8_t *in;            // raw bytes, or DVCL command-list blobs (include/divans_b200.h)
+    const uint64_t *in_off, *in_len;
+    int raw_mode;                 // 1: raw bytes + the internal literal-only command generator (raw_to_cmd/mod.rs:105-181)
+    uint32_t n_streams;
+    uint32_t *work_counter;
+    uint8_t *arena;
+    const uint8_t *tables;
+    const uint8_t *pm_internal;   // raw mode: the one PredictionMode record every stream starts with
+    uint32_t *sf; uint32_t cmd_cap, lit_cap;
+    uint32_t *sf_counts;          // per stream: [n_cmd_syms, n_lit_syms]
+    uint32_t *sf_dummy;           // per slot: where an idle group's core writes
+    uint8_t *replay; uint64_t replay_stride;   // per slot: the encoder replays its commands to mirror last_8_literals
+    uint32_t max_chunks;          // per stream: chunk records (cmd chunks first, then literal chunks)
+    uint32_t cmd_chunks;          //   = ceil(cmd_cap / 65536)
+    uint32_t *chunk_w;            // per chunk: first u32 entry of the chunk's renormalisation words (in place in the log)
+    uint8_t *chunk_state;         // per chunk: the 16 bytes of final states that precede them
+    uint8_t *out; const uint64_t *out_off, *out_cap; uint64_t *out_len;
+    int32_t *status;
+    // options (reference: DivansCompressorOptions, src/interface.rs:444-484)
+    int window_size, dynamic_context_mixing, prior_depth, use_context_map, force_stride, have_literal_adaptation;
+    int literal_adaptation[4];    // packed inc | lim << 16
+};
+constexpr uint32_t PM_RECORD_BYTES = 32 + 16384 + 1024 + 8192;
+
 // payload placement: stream i's two compacted byte streams live at payload + base(i): cmd first, lit at +align16(cmd bytes)
 __host__ __device__ inline uint64_t payload_base(uint64_t in_off, uint32_t i) { return (in_off + 48ull * i + 15ull) & ~15ull; }
 

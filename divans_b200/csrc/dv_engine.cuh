@@ -88,7 +88,8 @@ struct Cold {
     Weights w_lo, w_hi;                      // model_weights[0], [1]
     uint32_t mixing_param;
     bool lit_slabs_ready;
-    uint32_t out_cap, ring_len;
+    uint32_t out_cap, ring_len, raw_len;
+    uint32_t lit_log_cap;                    // encoder: capacity (entries) of the literal coder's log
     uint32_t sidx;                           // stream index being processed
     // encoder
     CmdIn in;

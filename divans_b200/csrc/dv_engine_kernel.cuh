@@ -4,43 +4,33 @@
 
 namespace dv {
 
-struct EncodeParams {
-    // DVCL blobs (include/divans_b200.h) or raw inputs with the internal literal-only command generator
-    const uint8_t *in;
-    const uint64_t *in_off, *in_len;
-    int raw_mode;                 // 1: `in` holds raw bytes (raw_to_cmd/mod.rs:105-181), 0: DVCL command lists
-    uint32_t n_streams;
-    uint32_t *work_counter;
-    uint8_t *arena;
-    const uint8_t *tables;
-    uint32_t *sf;                 // per slot: (start|freq<<16) logs, cmd then lit
-    uint64_t sf_stride;           // entries per slot (both coders)
-    uint32_t *sf_counts;          // per stream: [n_cmd_syms, n_lit_syms]
-    uint8_t *replay;              // per slot: window replay buffer (the encoder keeps the ring to mirror last_8_literals)
-    uint64_t replay_stride;
-    int32_t *status;
-    // options (reference: DivansCompressorOptions, src/interface.rs:444-484)
-    int window_size, dynamic_context_mixing, prior_depth, use_context_map, force_stride, have_literal_adaptation;
-    int literal_adaptation[4];    // packed inc|lim<<16
-    int literal_pred_mode, literal_mixing_value;
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // transition helpers (all force-inlined into the kernel; St lives in registers)
 // ---------------------------------------------------------------------------------------------------------------
+// Fetch the next input command (encoder).  Either a record of the DVCL blob, or -- raw mode -- the commands of the
+// reference's internal literal-only generator (raw_to_cmd/mod.rs:105-181): one PredictionMode, then one Literal per
+// ring-buffer fill.
 template <bool ENC>
-__device__ __forceinline__ void load_cmd(St &s) {
-    if (ENC && s.c->in.pos < s.c->in.n_cmds) {
-        const uint32_t *c = s.c->in.cmds + 5 * (size_t)s.c->in.pos;
+__device__ __forceinline__ int load_cmd(St &s) {
+    if (!ENC) return 0;
+    const uint32_t pos = s.c->in.pos;
+    if (s.c->in.cmds) {
+        const uint32_t *c = s.c->in.cmds + 5 * (size_t)pos;
         s.c->e0 = c[1]; s.c->e1 = c[2]; s.c->e2 = c[3]; s.c->e3 = c[4];
+        return (int)c[0];
     }
+    if (pos == 0) { s.c->e0 = 0; s.c->e1 = 0; s.c->e2 = 0; s.c->e3 = 0; return 7; }
+    const uint32_t off = (pos - 1) * s.c->ring_len;
+    s.c->e0 = off; s.c->e1 = min(s.c->ring_len, s.c->raw_len - off); s.c->e2 = 0; s.c->e3 = 0;
+    return 3;
 }
 template <bool ENC>
 __device__ __forceinline__ void enter_cmd_type(St &s, Next &nx) {
     s.state = S_CMD_TYPE;
     nx.cdf = A_misc(s, MI_CC + (int)(s.c->last_4_states >> 4)); nx.cdf2 = nullptr; nx.speed = SPK_ROCKET;
     if (ENC) {
-        if (s.c->in.pos < s.c->in.n_cmds) { nx.sym = (int)s.c->in.cmds[5 * (size_t)s.c->in.pos]; load_cmd<ENC>(s); }
+        if (s.c->in.pos < s.c->in.n_cmds) nx.sym = load_cmd<ENC>(s);
         else nx.sym = 0xf;   // end of stream nibble (codec/mod.rs:143-148, flush :424-455)
     }
 }
@@ -119,7 +109,11 @@ __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint3
     s.l8 = reseed_last8(s);
     swap_coders(s);
     s.lit_left = len;
-    if (ENC) s.c->e1 = len;
+    if (ENC) {
+        s.c->e1 = len;
+        // hostile command lists: the literal must lie inside the pool and its nibbles inside the log
+        if ((uint64_t)s.c->e0 + len > s.c->raw_len || (uint64_t)s.cur.left + 2ull * len > s.c->lit_log_cap) { s.status = ST_FAIL; return; }
+    }
     lit_context(s);
     enter_lit_nibble<ENC, true>(s, nx);
 }

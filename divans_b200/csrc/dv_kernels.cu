@@ -1,6 +1,5 @@
 // dv_kernels.cu -- sm_100a kernels of the divANS batch engine: framing/CRC pre-pass and the stream decoder.
-#include "dv_engine_kernel.cuh"
-#include "dv_kernels.h"
+#include "dv_core.cuh"
 
 namespace dv {
 
@@ -8,9 +7,6 @@ namespace dv {
 // frame kernel: one thread per stream walks the 16-byte header and the mux record chain (mux.rs:384-444) to the
 // EOF marker, checks the trailer magic and the CRC32C of header..EOF marker (codec/decoder.rs:186-213).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t crc_step(const uint32_t *tab, uint32_t crc, uint32_t byte) {
-    return tab[(crc ^ byte) & 0xff] ^ (crc >> 8);
-}
 #if DV_LPS == 32
 __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
     __shared__ uint32_t tab[4][256];   // slice-by-4 tables for the Castagnoli polynomial (reflected 0x82F63B78)
@@ -141,190 +137,6 @@ __global__ void __launch_bounds__(128) demux_kernel(FrameParams p, uint8_t *payl
 // stream kernel: persistent warps, two streams per warp in lock step (dv_engine.cuh), work pulled from a global counter.
 // LPS == 32 keeps the north-star "one warp owns one stream" layout: the upper half-warp mirrors the lower one.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SMEM_BYTES_PER_GROUP = (int)((sizeof(Cold) + 15) / 16 * 16);
-
-// The converged nibble core.  Every lane of the warp executes it every iteration, unpredicated: a group without work
-// codes against its slot's dummy CDF with a parked coder (no memory side effects that matter).
-template <bool ENC, int LPS>
-__device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, const bool writer) {
-    const Grp gg = {FULL, g.shift, g.l16, writer, false, g.store0};
-    const int c = nx.cdf[g.l16], maxv = nx.cdf[15];
-    const int inc = (int)(short)(nx.speed & 0xffff), lim = nx.speed >> 16;
-    int sym, start, freq;
-    if (!__any_sync(FULL, nx.cdf2 != nullptr)) {
-        if (!ENC) {
-            coder_fill(s.cur);
-            int off = (int)(s.cur.a & 0x7fff);
-            int r = (int)(short)((off * maxv) >> 15);                       // probability/interface.rs:140
-            bool pred = (g.l16 == 15) || (r < c);
-            unsigned bal = __ballot_sync(FULL, pred);
-            sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
-        } else sym = nx.sym;
-        int cum = cdf_div(c, maxv);
-        int hi = __shfl_sync(FULL, cum, sym, 16);
-        int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
-        if (sym == 0) lo = 0;
-        start = (int)(short)(lo + 1); freq = (int)(short)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
-        if (!ENC) coder_advance(s.cur, start, freq);
-        else { if (g.store0) const_cast<uint32_t *>(s.cur.p)[s.cur.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); s.cur.left++; }
-        int c2 = cdf_blend(gg, c, maxv, sym, inc, lim);
-        if (writer) nx.cdf[g.l16] = (int16_t)c2;
-        return sym;
-    }
-    // ---- at least one group mixes two priors (dynamic context mixing >= 2, codec/literal.rs:219-243) ----
-    const bool mixg = nx.cdf2 != nullptr;
-    int cc = c, mc = maxv;
-    if (mixg) { cc = nx.cdf2[g.l16]; mc = nx.cdf2[15]; }
-    Weights w = nx.mix_hi ? s.c->w_hi : s.c->w_lo;
-    int prod = mc * maxv;
-    int lz = prod == 0 ? 32 : __clz(prod); if (lz > 17) lz = 17;
-    int shift = 17 - lz;
-    int mixr = w.norm, inv = (1 << 15) - mixr;
-    int rs = (cc * maxv) >> shift, ro = (c * mc) >> shift;
-    int ca = (int)(short)((int)((unsigned)rs * (unsigned)mixr + (unsigned)ro * (unsigned)inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
-    int ma = __shfl_sync(FULL, ca, 15, 16);
-    int cu = mixg ? ca : c, mu = mixg ? ma : maxv;
-    if (!ENC) {
-        coder_fill(s.cur);
-        int off = (int)(s.cur.a & 0x7fff);
-        int r = (int)(short)((off * mu) >> 15);
-        bool pred = (g.l16 == 15) || (r < cu);
-        unsigned bal = __ballot_sync(FULL, pred);
-        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
-    } else sym = nx.sym;
-    int cum = cdf_div(cu, mu);
-    int hi = __shfl_sync(FULL, cum, sym, 16);
-    int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
-    if (sym == 0) lo = 0;
-    start = (int)(short)(lo + 1); freq = (int)(short)(hi - lo - 1);
-    int f_cm = cdf_freq(gg, cc, mc, sym);
-    int f_nb = cdf_freq(gg, c, maxv, sym);
-    if (!ENC) coder_advance(s.cur, start, freq);
-    else { if (g.store0) const_cast<uint32_t *>(s.cur.p)[s.cur.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); s.cur.left++; }
-    if (mixg) {
-        weights_update(w, f_cm, f_nb, freq);
-        if (nx.mix_hi) s.c->w_hi = w; else s.c->w_lo = w;
-        const int sp = nx.mix_hi ? s.c->ad_cm_hi : s.c->ad_cm_lo;
-        int c2 = cdf_blend(gg, cc, mc, sym, (int)(short)(sp & 0xffff), sp >> 16);
-        if (writer) nx.cdf2[g.l16] = (int16_t)c2;
-    }
-    int s2 = cdf_blend(gg, c, maxv, sym, inc, lim);
-    if (writer) nx.cdf[g.l16] = (int16_t)s2;
-    return sym;
-}
-
-// Plain (non-mixing) nibble step split in three phases so that the literal fast path can software-pipeline it:
-//   lit_load   issue the two loads of the prior (element l16 and the maximum)
-//   lit_search refill the rANS state if needed and find the symbol (ballot)       -- on the critical path
-//   lit_finish exact start/freq, rANS state update, adaptive blend, store         -- off the critical path
-struct CdfRegs { int c, maxv; };
-__device__ __forceinline__ CdfRegs lit_load(const G2 g, const int16_t *cdf) { CdfRegs r; r.c = cdf[g.l16]; r.maxv = cdf[15]; return r; }
-template <bool ENC>
-__device__ __forceinline__ int lit_search(Coder &k, const G2 g, const CdfRegs r, const int sym_in) {
-    if (ENC) return sym_in;
-    coder_fill(k);
-    int off = (int)(k.a & 0x7fff);
-    int rr = (int)(short)((off * r.maxv) >> 15);                      // probability/interface.rs:140
-    bool pred = (g.l16 == 15) || (rr < r.c);
-    unsigned bal = __ballot_sync(FULL, pred);
-    return __ffs((bal >> g.shift) & 0xffffu) - 1;
-}
-template <bool ENC>
-__device__ __forceinline__ void lit_finish(Coder &k, const G2 g, const bool writer, int16_t *cdf, const CdfRegs r, const int sym, const int inc, const int lim) {
-    int cum = cdf_div(r.c, r.maxv);
-    int hi = __shfl_sync(FULL, cum, sym, 16);
-    int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
-    if (sym == 0) lo = 0;
-    int start = (int)(short)(lo + 1), freq = (int)(short)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
-    if (!ENC) coder_advance(k, start, freq);
-    else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
-    int c2 = (int)(short)(r.c + ((g.l16 >= sym) ? inc : 0));
-    if ((int)(short)(r.maxv + inc) >= lim) { int t = (int)(short)(c2 + g.l16 + 1); c2 = (int)(short)(t - (t >> 2)); }
-    if (writer) cdf[g.l16] = (int16_t)c2;
-}
-
-// Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
-// (high nibble, low nibble, context of the next byte) back to back without going through the state-machine dispatch.
-// This is code_nibble_array (codec/literal.rs:261-394) for two streams at once.  The common case -- no dynamic context
-// mixing and one mixing-mask value for the whole map -- gets a loop with every selector hoisted out.
-template <bool ENC, int LPS>
-__device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const bool writer) {
-    uint32_t n = s.lit_left;
-    if (LPS == 16) n = min(n, __shfl_xor_sync(FULL, n, 16));
-    const bool simple = __all_sync(FULL, !s.mixing_trait && s.lit_cfg >= 0);
-    if (simple) {
-        const int cfg = s.lit_cfg;
-        const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;
-        const uint32_t sh = (uint32_t)(cfg >> 2) & 63u, which = (uint32_t)cfg & 3u;
-        const bool ro = (cfg & 0x800) != 0;
-        const int inc = ro ? 0 : (int)(short)(s.ad_stride & 0xffff), lim = ro ? 0x7fff : (s.ad_stride >> 16);
-        int16_t *const hi_base = A_lit(s, true) + (size_t)which * 256 * 256 * 16;
-        int16_t *const lo_base = A_lit(s, false) + (size_t)which * 256 * 256 * 16;
-        int16_t *const flat = A_misc(s, MI_FLAT);
-        const uint8_t *const lcm = A_lcm(s) + (s.btype_last << 6);
-        const uint8_t *const lut = s.tables + TB_CTX + 512 * s.pred_mode;
-        const uint32_t pm = s.pred_mode;
-        const uint8_t *src = ENC ? s.c->in.lits + s.c->e0 + (s.c->e1 - s.lit_left) : nullptr;
-        unsigned long long l8 = s.l8;
-        uint32_t ctx = s.lit_ctx;
-        uint8_t *dst = s.out + s.out_pos;
-        Coder k = s.cur;
-        // Software pipeline (the loads of the NEXT prior are issued before the bookkeeping of the CURRENT nibble):
-        //   search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo)
-        // The high and low tables never alias, so the early loads cannot overtake a store to the same CDF; the
-        // __syncwarp()s order each store against the next load of the same table across lanes.
-        int16_t *ph; int16_t *pl;
-        {
-            const uint32_t ssb0 = (uint32_t)(l8 >> sh) & 0xffu;
-            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssb0 & mm & (~o1 & 0xffu)))) * 16;
-        }
-        __syncwarp();
-        CdfRegs rh = lit_load(g, ph);
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
-            const uint32_t byte_in = ENC ? src[i] : 0u;
-            const int h = lit_search<ENC>(k, g, rh, (int)(byte_in >> 4));
-            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
-            pl = ro ? flat : lo_base + ((size_t)(ic * 256 + ib)) * 16;
-            __syncwarp();
-            const CdfRegs rl = lit_load(g, pl);
-            lit_finish<ENC>(k, g, writer, ph, rh, h, inc, lim);
-            const int l = lit_search<ENC>(k, g, rl, (int)(byte_in & 0xf));
-            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
-            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
-            if (g.store0) dst[i] = (uint8_t)cur;
-            uint32_t sel;                                         // get_prev_word_context, codec/literal.rs:87-117
-            if (pm == 0) sel = cur & 0x3f;
-            else if (pm == 1) sel = cur >> 2;
-            else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
-            ctx = lcm[sel];
-            const uint32_t ssbn = (uint32_t)(l8 >> sh) & 0xffu;
-            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssbn & mm & (~o1 & 0xffu)))) * 16;
-            __syncwarp();
-            rh = lit_load(g, ph);                                 // speculative on the last byte: a valid, initialised slab
-            lit_finish<ENC>(k, g, writer, pl, rl, l, inc, lim);
-        }
-        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
-        enter_lit_nibble<ENC, true>(s, nx);
-        return;
-    }
-    for (uint32_t i = 0; i < n; i++) {
-        __syncwarp();
-        int h = nibble_core<ENC, LPS>(s, nx, g, writer);
-        s.lit_h = (uint32_t)h;
-        enter_lit_nibble<ENC, false>(s, nx);
-        __syncwarp();
-        int l = nibble_core<ENC, LPS>(s, nx, g, writer);
-        uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
-        s.l8 = (s.l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
-        if (g.store0) s.out[s.out_pos] = (uint8_t)cur;
-        s.out_pos++;
-        s.lit_left--;
-        lit_context(s);
-        enter_lit_nibble<ENC, true>(s, nx);
-    }
-}
-
 template <int LPS>
 __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];

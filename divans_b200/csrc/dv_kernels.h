@@ -12,4 +12,7 @@ cudaError_t upload_ctx_lut32(const uint8_t *host2048);
 cudaError_t upload_ctx_lut16(const uint8_t *host2048);
 int decode_max_blocks_per_sm32();
 int decode_max_blocks_per_sm16();
+void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes
+void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st);                  // reverse rANS + mux/CRC (2 launches)
+int encode_max_blocks_per_sm();
 }  // namespace dv

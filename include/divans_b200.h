@@ -152,6 +152,13 @@ DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size_t n, const
                                            const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                            const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
                                            const divans_b200_encode_options *opts);
+/* Same as divans_b200_encode_batch_host with every pointer a DEVICE pointer (raw inputs resident in HBM, framed streams
+ * left in HBM); `max_in_len` >= every in_len[i] sizes the per-stream symbol logs.  Asynchronous on `cuda_stream`
+ * (NULL = the context's own stream); status/out_len are valid after divans_b200_synchronize / a stream sync. */
+DivansResult divans_b200_encode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                             const uint64_t *d_in_len, uint64_t max_in_len, uint8_t *d_out,
+                                             const uint64_t *d_out_off, const uint64_t *d_out_cap, uint64_t *d_out_len,
+                                             int32_t *d_status, const divans_b200_encode_options *opts, void *cuda_stream);
 /* Encode n command lists ("DVCL" blobs, below) held in HOST memory: the entropy-coding half for arbitrary IR. */
 DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *blobs, const uint64_t *blob_off,
                                                 const uint64_t *blob_len, uint8_t *out, const uint64_t *out_off,

@@ -1,0 +1,141 @@
+"""GPU encoder parity (-m gpu): the CUDA encoder (model pass + reverse rANS pass + mux/CRC pass), called through the
+C ABI, must produce byte-identical .divans streams to the CPU oracle's encoder on the same commands and options."""
+import io
+
+import numpy as np
+import pytest
+
+from irfuzz import random_ir
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def text():
+    from divans_b200 import synth
+    return synth.text_corpus(1 << 20)
+
+
+def _first_diff(a, b):
+    return next((k for k in range(min(len(a), len(b))) if a[k] != b[k]), min(len(a), len(b)))
+
+
+def _check(got, ref, what):
+    assert len(got) == len(ref) and got == ref, "%s: len %d vs %d, first diff at %d" % (what, len(got), len(ref), _first_diff(got, ref))
+
+
+OPTION_SETS = [
+    dict(),
+    dict(window_size=10),
+    dict(window_size=16, dynamic_context_mixing=1),
+    dict(dynamic_context_mixing=2),
+    dict(dynamic_context_mixing=3, prior_depth=2),
+    dict(force_stride=0),
+    dict(force_stride=3, use_context_map=1),
+    dict(use_context_map=0, dynamic_context_mixing=2),
+    dict(literal_adaptation=[(2, 1024), (16, 8192), (128, 16384), (1, 128)]),
+    dict(dynamic_context_mixing=2, literal_adaptation=[(32, 4096), (4, 1024), (64, 16384), (512, 16384)]),
+]
+
+
+@pytest.mark.parametrize("kw", OPTION_SETS, ids=lambda d: ",".join("%s=%s" % (k, v if not isinstance(v, list) else "set") for k, v in d.items()) or "default")
+def test_raw_encode_matches_oracle(engine, oracle, text, kw):
+    import divans_b200
+    rng = np.random.default_rng(5)
+    raws = [text[:n] for n in [0, 1, 2, 15, 16, 17, 1023, 1024, 1025, 4097, 40000]]
+    raws.append(rng.integers(0, 256, 3000).astype(np.uint8).tobytes())
+    raws.append(bytes(7000))
+    got = engine.encode(raws, divans_b200.encode_options(**kw))
+    for i, r in enumerate(raws):
+        _check(got[i], oracle.encode_raw(r, oracle.options(**kw)), "raw stream %d (len %d) opts %s" % (i, len(r), kw))
+
+
+def test_raw_encode_chunk_restart_and_big_records(engine, oracle, text):
+    # > 65536 literal nibbles (rANS chunk restart, ans.rs:57,138) and coder payloads > 65536 B (fixed-size mux records)
+    rng = np.random.default_rng(9)
+    raws = [text[:65535], text[:65536], text[:65537], text[:200000], rng.integers(0, 256, 150000).astype(np.uint8).tobytes(),
+            text[:32768] + rng.integers(0, 256, 140000).astype(np.uint8).tobytes()]
+    got = engine.encode(raws)
+    for i, r in enumerate(raws):
+        _check(got[i], oracle.encode_raw(r), "stream %d" % i)
+
+
+@pytest.mark.parametrize("pm", [0, 1, 2, 3])
+def test_raw_encode_prediction_modes(engine, oracle, text, pm):
+    import divans_b200
+    for mv in range(9):
+        r = text[5000 * mv: 5000 * mv + 4000]
+        out, off, ln = oracle.encode_batch(np.frombuffer(r, np.uint8), [0], [len(r)], oracle.options(), 1, False, pm, mv)
+        got = engine.encode([r], divans_b200.encode_options(literal_pred_mode=pm, literal_mixing_value=mv))
+        _check(got[0], out[: int(ln[0])].tobytes(), "pm %d mixing %d" % (pm, mv))
+
+
+def test_command_lists_lz77(engine, oracle, text):
+    import divans_b200
+    for win, pm, mv, kw in [(16, 2, 4, {}), (10, 0, 4, dict(window_size=10)), (16, 3, 1, dict(dynamic_context_mixing=2)),
+                            (16, 1, 6, dict(force_stride=2))]:
+        cls = [oracle.Commands.lz77(text[o:o + n], win, pm, mv) for o, n in [(0, 100), (500, 5000), (9000, 70000), (100000, 30000)]]
+        kw = dict(kw); kw.setdefault("window_size", win)
+        got = engine.encode([c.serialize() for c in cls], divans_b200.encode_options(**kw), cmds=True)
+        for i, c in enumerate(cls):
+            _check(got[i], c.encode(oracle.options(**kw)), "lz77 list %d win %d" % (i, win))
+
+
+def test_command_lists_random_ir(engine, oracle, text):
+    import divans_b200
+    cls, refs = [], []
+    for seed in range(24):
+        c = oracle.Commands.from_ir(random_ir(oracle, seed, n_cmds=150, window=16, text=text))
+        cls.append(c)
+    for kw in [dict(window_size=16), dict(window_size=16, dynamic_context_mixing=2, prior_depth=1), dict(window_size=16, force_stride=5)]:
+        got = engine.encode([c.serialize() for c in cls], divans_b200.encode_options(**kw), cmds=True)
+        for i, c in enumerate(cls):
+            _check(got[i], c.encode(oracle.options(**kw)), "random IR seed %d opts %s" % (i, kw))
+
+
+def test_bad_command_list_is_rejected_not_crashing(engine):
+    blob = np.zeros(64, np.uint8)
+    out = np.zeros(1 << 16, np.uint8)
+    ln, st = engine.encode_batch_host(blob, [0], [64], out, [0], [1 << 16], None, cmds=True)
+    assert st[0] != 0
+
+
+def test_output_capacity_too_small(engine, oracle, text):
+    r = text[:5000]
+    ref = oracle.encode_raw(r)
+    out = np.zeros(1 << 16, np.uint8)
+    blob = np.frombuffer(r, np.uint8)
+    ln, st = engine.encode_batch_host(blob, [0], [len(r)], out, [0], [len(ref) - 1])
+    assert st[0] == 2 and int(ln[0]) == len(ref)      # NEEDS_MORE_OUTPUT + the size that would have been needed
+    ln, st = engine.encode_batch_host(blob, [0], [len(r)], out, [0], [len(ref)])
+    assert st[0] == 0 and out[: len(ref)].tobytes() == ref
+
+
+def test_reference_ffi_compressor_writer(engine, oracle, text):
+    import divans_b200
+    r = text[:100000]
+    sink = io.BytesIO()
+    w = divans_b200.DivansCompressorWriter(sink)
+    for o in range(0, len(r), 7777):
+        w.write(r[o:o + 7777])
+    w.close()
+    stream = sink.getvalue()
+    rc, back = oracle.decode(stream, out_cap=len(r) + 64)
+    assert rc == 0 and back == r
+    (st, out), = engine.decode([stream], [len(r) + 64])
+    assert st == 0 and out == r
+
+
+def test_full_size_encode_decode_round_trip(engine, oracle):
+    # BASELINE config 4 shape: 4096 x 64 KiB through the GPU encoder, back through the GPU decoder
+    import divans_b200
+    from divans_b200 import synth
+    n, size = 4096, 65536
+    corpus = synth.text_corpus(n * size // 4)
+    raws = [corpus[(i * size) % (len(corpus) - size): (i * size) % (len(corpus) - size) + size] for i in range(n)]
+    streams = engine.encode(raws, divans_b200.encode_options(window_size=16))
+    for i in [0, 1, n // 2, n - 1]:
+        _check(streams[i], oracle.encode_raw(raws[i], oracle.options(window_size=16)), "stream %d" % i)
+    res = engine.decode(streams, [size + 64] * n)
+    assert all(st == 0 for st, _ in res)
+    assert all(out == raws[i] for i, (_, out) in enumerate(res))
