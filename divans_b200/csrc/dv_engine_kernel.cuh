@@ -72,7 +72,7 @@ __device__ __forceinline__ void enter_lit_nibble(St &s, Next &nx) {
         nx.cdf2 = nullptr;
     }
     if (ENC) {
-        uint32_t byte = s.c->in.lits[s.c->e0 + (s.c->e1 - s.lit_left)];
+        uint32_t byte = s.lit_left ? s.c->in.lits[s.c->e0 + (s.c->e1 - s.lit_left)] : 0u;   // (called once more after the last byte)
         nx.sym = HIGH ? (int)(byte >> 4) : (int)(byte & 0xf);
     }
     s.state = HIGH ? S_LIT_HI : S_LIT_LO;
