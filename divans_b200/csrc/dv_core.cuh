@@ -112,6 +112,48 @@ __device__ __forceinline__ void lit_finish(Coder &k, const G2 g, const bool writ
     if (writer) cdf[g.l16] = (int16_t)c2;
 }
 
+// One literal nibble coded against the mix of two priors (dynamic context mixing >= 2, codec/literal.rs:219-259):
+// `nb` = the stride prior, `cm` = the context-map prior, weights `w` (model_weights[high nibble ? 1 : 0]).
+template <bool ENC>
+__device__ __forceinline__ int mix_nibble(Coder &k, const G2 g, const bool writer, int16_t *nb, int16_t *cm, Weights &w,
+                                          const int nb_inc, const int nb_lim, const int cm_inc, const int cm_lim, const int sym_in) {
+    const int c = nb[g.l16], maxv = nb[15], cc = cm[g.l16], mc = cm[15];
+    const int prod = mc * maxv;
+    int lz = prod == 0 ? 32 : __clz(prod); if (lz > 17) lz = 17;
+    const int shift = 17 - lz;
+    const int mixr = w.norm, inv = (1 << 15) - mixr;
+    const int rs = (cc * maxv) >> shift, ro = (c * mc) >> shift;
+    const int ca = (int)(short)((int)((unsigned)rs * (unsigned)mixr + (unsigned)ro * (unsigned)inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
+    const int ma = __shfl_sync(FULL, ca, 15, 16);
+    int sym;
+    if (!ENC) {
+        coder_fill(k);
+        const int off = (int)(k.a & 0x7fff);
+        const int r = (int)(short)((off * ma) >> 15);
+        const bool pred = (g.l16 == 15) || (r < ca);
+        const unsigned bal = __ballot_sync(FULL, pred);
+        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
+    } else sym = sym_in;
+    // cumulative values of the three CDFs at sym and sym-1: two registers, four shuffles
+    const int cum_a = cdf_div(ca, ma);
+    const int cum_pn = cdf_div(cc, mc) | (cdf_div(c, maxv) << 16);
+    const int prev = (sym - 1) & 15;
+    const int hi_a = __shfl_sync(FULL, cum_a, sym, 16), hi_pn = __shfl_sync(FULL, cum_pn, sym, 16);
+    int lo_a = __shfl_sync(FULL, cum_a, prev, 16), lo_pn = __shfl_sync(FULL, cum_pn, prev, 16);
+    if (sym == 0) { lo_a = 0; lo_pn = 0; }
+    const int start = (int)(short)(lo_a + 1), freq = (int)(short)(hi_a - lo_a - 1);
+    const int f_cm = (int)(short)((hi_pn & 0xffff) - (lo_pn & 0xffff) - 1);
+    const int f_nb = (int)(short)(((unsigned)hi_pn >> 16) - ((unsigned)lo_pn >> 16) - 1);
+    if (!ENC) coder_advance(k, start, freq);
+    else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
+    weights_update32(w, f_cm, f_nb, freq);
+    const Grp gg = {FULL, g.shift, g.l16, writer, false, g.store0};
+    const int c2 = cdf_blend(gg, cc, mc, sym, cm_inc, cm_lim);
+    const int s2 = cdf_blend(gg, c, maxv, sym, nb_inc, nb_lim);
+    if (writer) { cm[g.l16] = (int16_t)c2; nb[g.l16] = (int16_t)s2; }
+    return sym;
+}
+
 // Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
 // (high nibble, low nibble, context of the next byte) back to back without going through the state-machine dispatch.
 // This is code_nibble_array (codec/literal.rs:261-394) for two streams at once.  The common case -- no dynamic context
@@ -174,6 +216,51 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
             lit_finish<ENC>(k, g, writer, pl, rl, l, inc, lim);
         }
         s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
+        enter_lit_nibble<ENC, true>(s, nx);
+        return;
+    }
+    if (__all_sync(FULL, s.mixing_trait && s.lit_cfg >= 0)) {
+        // every group mixes the stride prior with the context-map prior, one mixing-mask value for the whole map
+        const int cfg = s.lit_cfg;
+        const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;
+        const uint32_t sh = (uint32_t)(cfg >> 2) & 63u, which = (uint32_t)cfg & 3u;
+        const bool ro = (cfg & 0x800) != 0;
+        const int inc = ro ? 0 : (int)(short)(s.ad_stride & 0xffff), lim = ro ? 0x7fff : (s.ad_stride >> 16);
+        const int ch_inc = (int)(short)(s.c->ad_cm_hi & 0xffff), ch_lim = s.c->ad_cm_hi >> 16;
+        const int cl_inc = (int)(short)(s.c->ad_cm_lo & 0xffff), cl_lim = s.c->ad_cm_lo >> 16;
+        int16_t *const hi_base = A_lit(s, true) + (size_t)which * 256 * 256 * 16;
+        int16_t *const lo_base = A_lit(s, false) + (size_t)which * 256 * 256 * 16;
+        int16_t *const cmb = A_litcm(s);
+        const uint8_t *const lcm = A_lcm(s) + (s.btype_last << 6);
+        const uint8_t *const lut = s.tables + TB_CTX + 512 * s.pred_mode;
+        const uint32_t pm = s.pred_mode;
+        const uint8_t *src = ENC ? s.c->in.lits + s.c->e0 + (s.c->e1 - s.lit_left) : nullptr;
+        unsigned long long l8 = s.l8;
+        uint32_t ctx = s.lit_ctx;
+        uint8_t *dst = s.out + s.out_pos;
+        Coder k = s.cur;
+        Weights wh = s.c->w_hi, wl = s.c->w_lo;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
+            const uint32_t byte_in = ENC ? src[i] : 0u;
+            __syncwarp();
+            const int h = mix_nibble<ENC>(k, g, writer, hi_base + ((size_t)(ctx * 256 + (ssb & mm & (~o1 & 0xffu)))) * 16, cmb + (size_t)ctx * 16,
+                                          wh, inc, lim, ch_inc, ch_lim, (int)(byte_in >> 4));
+            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
+            __syncwarp();
+            const int l = mix_nibble<ENC>(k, g, writer, lo_base + ((size_t)(ic * 256 + ib)) * 16, cmb + (size_t)(256 + h + 16 * ctx) * 16,
+                                          wl, inc, lim, cl_inc, cl_lim, (int)(byte_in & 0xf));
+            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);
+            if (g.store0) dst[i] = (uint8_t)cur;
+            uint32_t sel;
+            if (pm == 0) sel = cur & 0x3f;
+            else if (pm == 1) sel = cur >> 2;
+            else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+            ctx = lcm[sel];
+        }
+        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
+        s.c->w_hi = wh; s.c->w_lo = wl;
         enter_lit_nibble<ENC, true>(s, nx);
         return;
     }

@@ -146,4 +146,33 @@ __device__ __forceinline__ void weights_update(Weights &w, int f_cm, int f_nb, i
     w.norm = (int)(unsigned short)(q << 7);
 }
 
+// 32-bit restatement of weights_update for the literal fast path.  Identical results whenever the coded frequencies
+// are in 1..32767 (always true for streams an encoder can produce): efficacy = 2^15 * (prob - p1) and
+// prod = p0 * efficacy, so prod >> lg is (p0 * (prob - p1)) shifted by (15 - lg) -- no 64-bit arithmetic needed.
+__device__ __forceinline__ int weights_new32(int prob, int p1, int wi) {
+    const int p0 = (1 << 15) - p1;
+    const int t = p0 * (prob - p1);
+    const unsigned geo = (unsigned)(p1 * p0);
+    const int lg = geo ? 32 - __clz((int)geo) : 0;
+    const int adj = lg <= 15 ? (int)((unsigned)t << (15 - lg)) : (t >> (lg - 15));
+    const int nw = (int)((unsigned)wi + (unsigned)adj);
+    return nw > 1 ? nw : 1;
+}
+__device__ __forceinline__ void weights_update32(Weights &w, int f_cm, int f_nb, int weighted) {
+    if (((w.w0 | w.w1) & 0x7f000000) != 0) {   // fix_weights, codec/weights.rs:64-79
+        int ilog = 32 - min(__clz(w.w0), __clz(w.w1));
+        if (ilog >= 24) { w.w0 >>= ilog - 24; w.w1 >>= ilog - 24; }
+    }
+    const int n0 = weights_new32(f_cm, weighted, w.w0);
+    const int n1 = weights_new32(f_nb, weighted, w.w1);
+    w.w0 = n0; w.w1 = n1;
+    const unsigned total = (unsigned)n0 + (unsigned)n1;       // compute_normalized_weight, :54-62 (total < 2^32)
+    const int shift = max(24 - __clz((int)total), 0);
+    const unsigned d = (total >> shift) & 0xffu;
+    const int recip = d ? 1 + cdf_div(512, (int)d) : 0;       // RECIPROCAL8[d] = 1 + 2^24 / d (div_lut.rs)
+    const unsigned num = ((unsigned)(n0 >> shift) << 8) & 0xffffu;
+    const int q = (int)(short)(((unsigned long long)(unsigned)recip * num) >> 24);
+    w.norm = (int)(unsigned short)(q << 7);
+}
+
 }  // namespace dv
