@@ -86,6 +86,8 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
 //   lit_load   issue the two loads of the prior (element l16 and the maximum)
 //   lit_search refill the rANS state if needed and find the symbol (ballot)       -- on the critical path
 //   lit_finish exact start/freq, rANS state update, adaptive blend, store         -- off the critical path
+// sign-extending 16-bit load (LDG.E.S16: no separate PRMT); ordered against the surrounding stores by the memory clobber
+__device__ __forceinline__ int ld_s16(const char *p) { int v; asm volatile("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 struct CdfRegs { int c, maxv; };
 __device__ __forceinline__ CdfRegs lit_load(const G2 g, const int16_t *cdf) { CdfRegs r; r.c = cdf[g.l16]; r.maxv = cdf[15]; return r; }
 template <bool ENC>
@@ -167,11 +169,11 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         const int cfg = s.lit_cfg;
         const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;
         const uint32_t sh = (uint32_t)(cfg >> 2) & 63u, which = (uint32_t)cfg & 3u;
-        const bool ro = (cfg & 0x800) != 0;
+        const bool ro = (cfg & 0x800) != 0;   // mixing value 2: the flat prior, never adapted (one CDF, index scale 0)
         const int inc = ro ? 0 : (int)(short)(s.ad_stride & 0xffff), lim = ro ? 0x7fff : (s.ad_stride >> 16);
-        int16_t *const hi_base = A_lit(s, true) + (size_t)which * 256 * 256 * 16;
-        int16_t *const lo_base = A_lit(s, false) + (size_t)which * 256 * 256 * 16;
-        int16_t *const flat = A_misc(s, MI_FLAT);
+        const uint32_t scale = ro ? 0u : 32u;
+        char *const hi_tab = ro ? reinterpret_cast<char *>(A_misc(s, MI_FLAT)) : reinterpret_cast<char *>(A_lit(s, true) + (size_t)which * 256 * 256 * 16);
+        char *const lo_tab = ro ? reinterpret_cast<char *>(A_misc(s, MI_FLAT)) : reinterpret_cast<char *>(A_lit(s, false) + (size_t)which * 256 * 256 * 16);
         const uint8_t *const lcm = A_lcm(s) + (s.btype_last << 6);
         const uint8_t *const lut = s.tables + TB_CTX + 512 * s.pred_mode;
         const uint32_t pm = s.pred_mode;
@@ -180,42 +182,117 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         uint32_t ctx = s.lit_ctx;
         uint8_t *dst = s.out + s.out_pos;
         Coder k = s.cur;
-        // Software pipeline (the loads of the NEXT prior are issued before the bookkeeping of the CURRENT nibble):
-        //   search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo)
-        // The high and low tables never alias, so the early loads cannot overtake a store to the same CDF; the
-        // __syncwarp()s order each store against the next load of the same table across lanes.
-        int16_t *ph; int16_t *pl;
-        {
-            const uint32_t ssb0 = (uint32_t)(l8 >> sh) & 0xffu;
-            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssb0 & mm & (~o1 & 0xffu)))) * 16;
+        // ---- decoder: switch the coder to EAGER refill for the duration of the loop ----
+        // The reference refills a state right before it is used (ans.rs:428-442); the word order in the stream is the
+        // order in which states were produced, so refilling a state as soon as it drops below 2^31 consumes the same
+        // words.  The literal coder codes nibbles in pairs: state `a` serves every high nibble, `b` every low nibble
+        // (two rotations of ans.rs:240-243 are the identity), so the loop never swaps them.
+        // Payload words are addressed by a saturating index: the demux kernel leaves >= 16 readable bytes after every
+        // coder's payload, so index n_words may be read once; an index that ends above n_words means underflow.
+        const uint32_t *const wbase = k.p;
+        const uint32_t wmax = k.left + 1;
+        uint32_t wi = 0;
+        if (!ENC) {
+            coder_fill(k);                                        // pending refill / 16-byte (re)initialisation of `a`
+            wi = (uint32_t)(k.p - wbase);
+            if (k.need_b) { k.b = (k.b << 32) | (uint64_t)wbase[wi]; wi = min(wi + 1, wmax); k.need_b = 0; }
         }
-        __syncwarp();
-        CdfRegs rh = lit_load(g, ph);
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
-            const uint32_t byte_in = ENC ? src[i] : 0u;
-            const int h = lit_search<ENC>(k, g, rh, (int)(byte_in >> 4));
-            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
-            pl = ro ? flat : lo_base + ((size_t)(ic * 256 + ib)) * 16;
+        uint32_t done = 0;
+        while (done < n) {
+            uint32_t m = n - done;
+            if (!ENC) {
+                if (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) {   // chunk restart, ans.rs:173-189
+                    if (wi + 5 <= wmax) { k.a = (uint64_t)wbase[wi] | ((uint64_t)wbase[wi + 1] << 32); k.b = (uint64_t)wbase[wi + 2] | ((uint64_t)wbase[wi + 3] << 32); wi += 4; }
+                    else { k.a = k.b = 0; wi = wmax; }
+                    k.sym_count = 0;
+                }
+                m = min(m, (NUM_SYMBOLS_BEFORE_FLUSH - k.sym_count) >> 1);
+                if (LPS == 16) m = min(m, __shfl_xor_sync(FULL, m, 16));
+                if (m == 0) break;   // unreachable: the literal coder codes nibbles in pairs, sym_count stays even
+            }
+            // Software pipeline (the loads of the NEXT prior are issued before the bookkeeping of the CURRENT nibble):
+            //   search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo)
+            // The high and low tables never alias, so the early loads cannot overtake a store to the same CDF; the
+            // __syncwarp()s order each store against the next load of the same table across lanes.
+            // Adaptive values stay below 2^15 for every speed an encoder can select (limit <= 0x4000 + increment), so the
+            // loop uses plain 32-bit arithmetic where the reference wraps i16.
+            char *ph = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * scale;
             __syncwarp();
-            const CdfRegs rl = lit_load(g, pl);
-            lit_finish<ENC>(k, g, writer, ph, rh, h, inc, lim);
-            const int l = lit_search<ENC>(k, g, rl, (int)(byte_in & 0xf));
-            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
-            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
-            if (g.store0) dst[i] = (uint8_t)cur;
-            uint32_t sel;                                         // get_prev_word_context, codec/literal.rs:87-117
-            if (pm == 0) sel = cur & 0x3f;
-            else if (pm == 1) sel = cur >> 2;
-            else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
-            ctx = lcm[sel];
-            const uint32_t ssbn = (uint32_t)(l8 >> sh) & 0xffu;
-            ph = ro ? flat : hi_base + ((size_t)(ctx * 256 + (ssbn & mm & (~o1 & 0xffu)))) * 16;
-            __syncwarp();
-            rh = lit_load(g, ph);                                 // speculative on the last byte: a valid, initialised slab
-            lit_finish<ENC>(k, g, writer, pl, rl, l, inc, lim);
+            int ch = ld_s16(ph + 2 * g.l16), mh = ld_s16(ph + 30);
+            for (uint32_t i = 0; i < m; i++) {
+                const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
+                const uint32_t byte_in = ENC ? src[done + i] : 0u;
+                // -- high nibble: search
+                int h;
+                if (!ENC) {
+                    const int rr = ((int)((uint32_t)k.a & 0x7fffu) * mh) >> 15;                    // probability/interface.rs:140
+                    h = __ffs((__ballot_sync(FULL, (g.l16 == 15) || (rr < ch)) >> g.shift) & 0xffffu) - 1;
+                } else h = (int)(byte_in >> 4);
+                const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
+                char *const pl = lo_tab + (ic * 256u + ib) * scale;
+                __syncwarp();
+                const int cl = ld_s16(pl + 2 * g.l16), ml = ld_s16(pl + 30);
+                // -- high nibble: finish
+                {
+                    const int cum = cdf_div(ch, mh);
+                    const int hi = __shfl_sync(FULL, cum, h, 16);
+                    int lo = __shfl_sync(FULL, cum, (h - 1) & 15, 16);
+                    if (h == 0) lo = 0;
+                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1) & 0xffffu;   // "major hax", probability/interface.rs:103-104
+                    if (!ENC) {
+                        const uint32_t t = ((uint32_t)k.a & 0x7fffu) - start;                      // 0 <= t < freq (the search put the offset in this bin)
+                        uint64_t x = (uint64_t)freq * (k.a >> 15) + (uint64_t)t;                    // ans.rs:230-244
+                        if (x < (1ull << 31)) { x = (x << 32) | (uint64_t)wbase[wi]; wi = min(wi + 1, wmax); }
+                        k.a = x;
+                    } else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = (start & 0xffffu) | (freq << 16); k.left++; }
+                    int c2 = ch + ((g.l16 >= h) ? inc : 0);
+                    if (mh + inc >= lim) { const int t = c2 + g.l16 + 1; c2 = t - (t >> 2); }
+                    if (writer) *reinterpret_cast<int16_t *>(ph + 2 * g.l16) = (int16_t)c2;
+                }
+                // -- low nibble: search
+                int l;
+                if (!ENC) {
+                    const int rr = ((int)((uint32_t)k.b & 0x7fffu) * ml) >> 15;
+                    l = __ffs((__ballot_sync(FULL, (g.l16 == 15) || (rr < cl)) >> g.shift) & 0xffffu) - 1;
+                } else l = (int)(byte_in & 0xf);
+                const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+                l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
+                if (g.store0) dst[done + i] = (uint8_t)cur;
+                uint32_t sel;                                         // get_prev_word_context, codec/literal.rs:87-117
+                if (pm == 0) sel = cur & 0x3f;
+                else if (pm == 1) sel = cur >> 2;
+                else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+                ctx = lcm[sel];
+                ph = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * scale;
+                __syncwarp();
+                ch = ld_s16(ph + 2 * g.l16); mh = ld_s16(ph + 30);   // speculative on the last byte: a valid, initialised slab
+                // -- low nibble: finish
+                {
+                    const int cum = cdf_div(cl, ml);
+                    const int hi = __shfl_sync(FULL, cum, l, 16);
+                    int lo = __shfl_sync(FULL, cum, (l - 1) & 15, 16);
+                    if (l == 0) lo = 0;
+                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1) & 0xffffu;
+                    if (!ENC) {
+                        const uint32_t t = ((uint32_t)k.b & 0x7fffu) - start;
+                        uint64_t x = (uint64_t)freq * (k.b >> 15) + (uint64_t)t;
+                        if (x < (1ull << 31)) { x = (x << 32) | (uint64_t)wbase[wi]; wi = min(wi + 1, wmax); }
+                        k.b = x;
+                    } else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = (start & 0xffffu) | (freq << 16); k.left++; }
+                    int c2 = cl + ((g.l16 >= l) ? inc : 0);
+                    if (ml + inc >= lim) { const int t = c2 + g.l16 + 1; c2 = t - (t >> 2); }
+                    if (writer) *reinterpret_cast<int16_t *>(pl + 2 * g.l16) = (int16_t)c2;
+                }
+            }
+            done += m;
+            if (!ENC) k.sym_count += 2 * m;
         }
-        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
+        if (!ENC) {   // back to the lazy representation the state machine uses
+            if (wi >= wmax) { k.underflow = 1; wi = wmax - 1; }
+            k.p = wbase + wi; k.left = wmax - 1 - wi;
+            k.need_a = (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) ? 8u : 0u; k.need_b = 0;
+        }
+        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += done; s.lit_left -= done;
         enter_lit_nibble<ENC, true>(s, nx);
         return;
     }
