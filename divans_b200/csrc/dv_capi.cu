@@ -48,6 +48,7 @@ struct divans_b200_ctx {
     uint8_t *d_replay = nullptr; size_t replay_cap = 0;
     uint32_t *d_enc_scratch = nullptr; size_t enc_scratch_cap = 0;
     uint8_t *d_pm_internal = nullptr; std::vector<uint8_t> h_pm;
+    uint64_t *d_rcp15 = nullptr;
     bool main_end_is_evm1 = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, evm1 = nullptr;   // ev0 | frame kernel | evm | decode kernel | ev1
     float last_kernel_ms = 0.f;
@@ -125,7 +126,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evm) cudaEventDestroy(ctx->evm);
     if (ctx->evm1) cudaEventDestroy(ctx->evm1);
-    cudaFree(ctx->d_sf); cudaFree(ctx->d_replay); cudaFree(ctx->d_enc_scratch); cudaFree(ctx->d_pm_internal);
+    cudaFree(ctx->d_sf); cudaFree(ctx->d_replay); cudaFree(ctx->d_enc_scratch); cudaFree(ctx->d_pm_internal); cudaFree(ctx->d_rcp15);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -269,6 +270,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     size_t words = 2 * n + slots + n * (size_t)max_chunks + 4 * n * (size_t)max_chunks + 16;
     if (!grow(ctx, &ctx->d_enc_scratch, &ctx->enc_scratch_cap, words)) return DIVANS_FAILURE;
     if (!ctx->d_pm_internal) CK(cudaMalloc((void **)&ctx->d_pm_internal, PM_RECORD_BYTES));
+    if (!ctx->d_rcp15) { CK(cudaMalloc((void **)&ctx->d_rcp15, 32768 * sizeof(uint64_t))); launch_rcp15_init(ctx->d_rcp15, st); ctx->launches += 1; }
     if (raw_mode) {
         // raw_to_cmd/mod.rs:116-143: 64-entry identity literal map, 4 distance entries, one mixing value, speeds unset
         std::vector<uint8_t> &pm = ctx->h_pm;
@@ -290,6 +292,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     ep.chunk_w = w; w += n * (size_t)max_chunks;
     w = reinterpret_cast<uint32_t *>(((uintptr_t)w + 15) & ~(uintptr_t)15);
     ep.chunk_state = reinterpret_cast<uint8_t *>(w);
+    ep.rcp15 = ctx->d_rcp15;
     ep.replay = ctx->d_replay; ep.replay_stride = replay_stride;
     ep.max_chunks = max_chunks; ep.cmd_chunks = cmd_chunks;
     ep.out = d_out; ep.out_off = d_out_off; ep.out_cap = d_out_cap; ep.out_len = d_out_len; ep.status = d_status;

@@ -182,6 +182,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         uint32_t ctx = s.lit_ctx;
         uint8_t *dst = s.out + s.out_pos;
         Coder k = s.cur;
+        const uint32_t src_last = s.lit_left - 1;                   // (lit_left >= 1 here)
         // ---- decoder: switch the coder to EAGER refill for the duration of the loop ----
         // The reference refills a state right before it is used (ans.rs:428-442); the word order in the stream is the
         // order in which states were produced, so refilling a state as soon as it drops below 2^31 consumes the same
@@ -219,9 +220,11 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
             char *ph = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * scale;
             __syncwarp();
             int ch = ld_s16(ph + 2 * g.l16), mh = ld_s16(ph + 30);
+            uint32_t nxt_in = ENC ? src[done] : 0u;                   // encoder: the input byte is fetched one iteration ahead
             for (uint32_t i = 0; i < m; i++) {
                 const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
-                const uint32_t byte_in = ENC ? src[done + i] : 0u;
+                const uint32_t byte_in = nxt_in;
+                if (ENC) nxt_in = src[min(done + i + 1, src_last)];
                 // -- high nibble: search
                 int h;
                 if (!ENC) {

@@ -132,16 +132,15 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) encode_model_kernel(Enco
 // ---------------------------------------------------------------------------------------------------------------
 // reverse rANS pass.  thread <-> (stream, chunk record)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t div_by_u15(uint64_t x, uint32_t f, uint32_t &rem) {
-    // x < 2^63, 0 < f < 2^15: long division in 16-bit limbs with 32-bit hardware-friendly divides
-    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
-    const uint32_t q2 = hi / f, r2 = hi - q2 * f;
-    const uint32_t t1 = (r2 << 16) | (lo >> 16);
-    const uint32_t q1 = t1 / f, r1 = t1 - q1 * f;
-    const uint32_t t0 = (r1 << 16) | (lo & 0xffffu);
-    const uint32_t q0 = t0 / f;
-    rem = t0 - q0 * f;
-    return ((uint64_t)q2 << 32) | ((uint64_t)q1 << 16) | (uint64_t)q0;
+// st / f through a table of 64-bit reciprocals M[f] = floor((2^64 - 1) / f): q = mulhi64(st, M[f]) is the true
+// quotient or one less (st < 2^63), fixed by one remainder test.  The table load depends only on the log entry, so it
+// is off the state-to-state dependency chain.
+__device__ __forceinline__ uint64_t div_by_u15(uint64_t x, uint32_t f, uint64_t M, uint32_t &rem) {
+    uint64_t q = __umul64hi(x, M);
+    uint64_t r = x - q * (uint64_t)f;
+    if (r >= (uint64_t)f) { q++; r -= (uint64_t)f; }
+    rem = (uint32_t)r;
+    return q;
 }
 
 __global__ void __launch_bounds__(128) encode_flush_kernel(EncodeParams p) {
@@ -157,17 +156,63 @@ __global__ void __launch_bounds__(128) encode_flush_kernel(EncodeParams p) {
     uint32_t *sf = p.sf + (uint64_t)v * (p.cmd_cap + p.lit_cap) + (lit ? p.cmd_cap : 0);
     uint64_t sa = 1ull << 31, sb = 1ull << 31;
     uint32_t w = last;
-    for (uint32_t k = last; k-- > first;) {
-        const uint32_t e = sf[k];
-        const uint32_t f = (uint32_t)(int)(short)(e >> 16) & 0x7fffu;   // freq is 1..32767 for every prior the model can reach
-        const uint64_t start = (uint64_t)(int64_t)(short)(e & 0xffffu);
-        uint64_t st = sa;
-        if (st >= ((uint64_t)f << 48)) { sf[--w] = (uint32_t)st; st >>= 32; }   // ans.rs:330-344; w > k always
-        uint32_t rem;
-        const uint64_t q = div_by_u15(st, f ? f : 1u, rem);
-        const uint64_t x = (q << 15) + rem + start;
-        sa = sb; sb = x;
+    // one step of ans.rs:330-352 for state `st` and log entry `e`; a symbol emits at most one word and w > k always,
+    // so the renormalisation words are stacked in place at the top of the chunk's own log region
+#define DV_RANS_PUT(st, e, Mv)                                                                                   \
+    {                                                                                                          \
+        const uint32_t f_ = ((e) >> 16) & 0x7fffu;     /* freq is 1..32767 for every prior the model can reach */ \
+        const uint64_t start_ = (uint64_t)(int64_t)(short)((e) & 0xffffu);                                     \
+        if ((st) >= ((uint64_t)f_ << 48)) { sf[--w] = (uint32_t)(st); (st) >>= 32; }                           \
+        uint32_t rem_;                                                                                         \
+        const uint64_t q_ = div_by_u15((st), f_ ? f_ : 1u, (Mv), rem_);                                        \
+        (st) = (q_ << 15) + rem_ + start_;                                                                     \
     }
+    // Symbols are taken last -> first; symbol j (counted from the end) belongs to state a when j is even, to b when odd
+    // (the rotation of ans.rs:350-352).  The log entries and their reciprocals are fetched one block of 8 symbols ahead
+    // of the arithmetic, so the only serial chain left is state -> state.
+    constexpr int BLK = 8;
+    const uint32_t cnt = last - first;
+    const uint32_t n_blk = cnt / BLK;
+    uint32_t e[BLK]; uint64_t M[BLK];
+    uint32_t k = last;
+    if (n_blk) {
+#pragma unroll
+        for (int i = 0; i < BLK; i++) e[i] = sf[k - 1 - i];
+#pragma unroll
+        for (int i = 0; i < BLK; i++) { const uint32_t f_ = (e[i] >> 16) & 0x7fffu; M[i] = __ldg(p.rcp15 + (f_ ? f_ : 1u)); }
+    }
+    for (uint32_t blk = 0; blk < n_blk; blk++) {
+        uint32_t en[BLK]; uint64_t Mn[BLK];
+        const bool more = blk + 1 < n_blk;
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < BLK; i++) en[i] = sf[k - BLK - 1 - i];
+#pragma unroll
+            for (int i = 0; i < BLK; i++) { const uint32_t f_ = (en[i] >> 16) & 0x7fffu; Mn[i] = __ldg(p.rcp15 + (f_ ? f_ : 1u)); }
+        }
+#pragma unroll
+        for (int i = 0; i < BLK; i += 2) {
+            DV_RANS_PUT(sa, e[i], M[i])
+            DV_RANS_PUT(sb, e[i + 1], M[i + 1])
+        }
+        k -= BLK;
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < BLK; i++) { e[i] = en[i]; M[i] = Mn[i]; }
+        }
+    }
+    {   // tail: fewer than BLK symbols
+        bool use_a = true;
+        for (; k > first; k--) {
+            const uint32_t e1 = sf[k - 1];
+            const uint32_t f1 = (e1 >> 16) & 0x7fffu;
+            const uint64_t M1 = __ldg(p.rcp15 + (f1 ? f1 : 1u));
+            if (use_a) { DV_RANS_PUT(sa, e1, M1) } else { DV_RANS_PUT(sb, e1, M1) }
+            use_a = !use_a;
+        }
+        if (cnt & 1) { const uint64_t tmp = sa; sa = sb; sb = tmp; }   // odd count: the roles end up swapped
+    }
+#undef DV_RANS_PUT
     { const uint64_t tmp = sa; sa = sb; sb = tmp; }
     uint64_t *cs = reinterpret_cast<uint64_t *>(p.chunk_state + 16 * t);
     cs[0] = sa; cs[1] = sb;
@@ -289,6 +334,12 @@ void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t 
     size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP;
     encode_model_kernel<16><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
 }
+// M[f] = floor((2^64 - 1) / f), f = 1..32767 (entry 0 unused)
+__global__ void rcp15_init_kernel(uint64_t *tab) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < 32768) tab[f] = f ? 0xffffffffffffffffull / (uint64_t)f : 0ull;
+}
+void launch_rcp15_init(uint64_t *tab, cudaStream_t st) { rcp15_init_kernel<<<32768 / 256, 256, 0, st>>>(tab); }
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st) {
     const uint64_t items = (uint64_t)p.n_streams * p.max_chunks;
     encode_flush_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(p);

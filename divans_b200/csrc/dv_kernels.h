@@ -15,4 +15,5 @@ int decode_max_blocks_per_sm16();
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st);                  // reverse rANS + mux/CRC (2 launches)
 int encode_max_blocks_per_sm();
+void launch_rcp15_init(uint64_t *tab, cudaStream_t st);
 }  // namespace dv
