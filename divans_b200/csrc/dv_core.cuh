@@ -86,8 +86,6 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
 //   lit_load   issue the two loads of the prior (element l16 and the maximum)
 //   lit_search refill the rANS state if needed and find the symbol (ballot)       -- on the critical path
 //   lit_finish exact start/freq, rANS state update, adaptive blend, store         -- off the critical path
-// sign-extending 16-bit load (LDG.E.S16: no separate PRMT); ordered against the surrounding stores by the memory clobber
-__device__ __forceinline__ int ld_s16(const char *p) { int v; asm volatile("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 struct CdfRegs { int c, maxv; };
 __device__ __forceinline__ CdfRegs lit_load(const G2 g, const int16_t *cdf) { CdfRegs r; r.c = cdf[g.l16]; r.maxv = cdf[15]; return r; }
 template <bool ENC>
@@ -114,12 +112,15 @@ __device__ __forceinline__ void lit_finish(Coder &k, const G2 g, const bool writ
     if (writer) cdf[g.l16] = (int16_t)c2;
 }
 
+// sign-extending 16-bit load (LDG.E.S16: no separate PRMT); ordered against the surrounding stores by the memory clobber
+__device__ __forceinline__ int ld_s16(const char *p) { int v; asm volatile("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 // One literal nibble coded against the mix of two priors (dynamic context mixing >= 2, codec/literal.rs:219-259):
 // `nb` = the stride prior, `cm` = the context-map prior, weights `w` (model_weights[high nibble ? 1 : 0]).
 template <bool ENC>
-__device__ __forceinline__ int mix_nibble(Coder &k, const G2 g, const bool writer, int16_t *nb, int16_t *cm, Weights &w,
+__device__ __forceinline__ int mix_nibble(Coder &k, uint64_t &st, const uint32_t *const wbase, uint32_t &wi, const uint32_t wmax,
+                                          const G2 g, const bool writer, char *nb, char *cm, Weights &w,
                                           const int nb_inc, const int nb_lim, const int cm_inc, const int cm_lim, const int sym_in) {
-    const int c = nb[g.l16], maxv = nb[15], cc = cm[g.l16], mc = cm[15];
+    const int c = ld_s16(nb + 2 * g.l16), maxv = ld_s16(nb + 30), cc = ld_s16(cm + 2 * g.l16), mc = ld_s16(cm + 30);
     const int prod = mc * maxv;
     int lz = prod == 0 ? 32 : __clz(prod); if (lz > 17) lz = 17;
     const int shift = 17 - lz;
@@ -129,9 +130,7 @@ __device__ __forceinline__ int mix_nibble(Coder &k, const G2 g, const bool write
     const int ma = __shfl_sync(FULL, ca, 15, 16);
     int sym;
     if (!ENC) {
-        coder_fill(k);
-        const int off = (int)(k.a & 0x7fff);
-        const int r = (int)(short)((off * ma) >> 15);
+        const int r = (int)(short)(((int)((uint32_t)st & 0x7fffu) * ma) >> 15);
         const bool pred = (g.l16 == 15) || (r < ca);
         const unsigned bal = __ballot_sync(FULL, pred);
         sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
@@ -146,13 +145,17 @@ __device__ __forceinline__ int mix_nibble(Coder &k, const G2 g, const bool write
     const int start = (int)(short)(lo_a + 1), freq = (int)(short)(hi_a - lo_a - 1);
     const int f_cm = (int)(short)((hi_pn & 0xffff) - (lo_pn & 0xffff) - 1);
     const int f_nb = (int)(short)(((unsigned)hi_pn >> 16) - ((unsigned)lo_pn >> 16) - 1);
-    if (!ENC) coder_advance(k, start, freq);
-    else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
+    if (!ENC) {   // eager refill, see literal_fast
+        const uint32_t t = ((uint32_t)st & 0x7fffu) - (uint32_t)start;
+        uint64_t x = (uint64_t)((uint32_t)freq & 0xffffu) * (st >> 15) + (uint64_t)t;   // ans.rs:230-244
+        if (x < (1ull << 31)) { x = (x << 32) | (uint64_t)wbase[wi]; wi = min(wi + 1, wmax); }
+        st = x;
+    } else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
     weights_update32(w, f_cm, f_nb, freq);
     const Grp gg = {FULL, g.shift, g.l16, writer, false, g.store0};
     const int c2 = cdf_blend(gg, cc, mc, sym, cm_inc, cm_lim);
     const int s2 = cdf_blend(gg, c, maxv, sym, nb_inc, nb_lim);
-    if (writer) { cm[g.l16] = (int16_t)c2; nb[g.l16] = (int16_t)s2; }
+    if (writer) { *reinterpret_cast<int16_t *>(cm + 2 * g.l16) = (int16_t)c2; *reinterpret_cast<int16_t *>(nb + 2 * g.l16) = (int16_t)s2; }
     return sym;
 }
 
@@ -310,7 +313,8 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         const int cl_inc = (int)(short)(s.c->ad_cm_lo & 0xffff), cl_lim = s.c->ad_cm_lo >> 16;
         int16_t *const hi_base = A_lit(s, true) + (size_t)which * 256 * 256 * 16;
         int16_t *const lo_base = A_lit(s, false) + (size_t)which * 256 * 256 * 16;
-        int16_t *const cmb = A_litcm(s);
+        char *const cmb = reinterpret_cast<char *>(A_litcm(s));
+        char *const hi_tab = reinterpret_cast<char *>(hi_base), *const lo_tab = reinterpret_cast<char *>(lo_base);
         const uint8_t *const lcm = A_lcm(s) + (s.btype_last << 6);
         const uint8_t *const lut = s.tables + TB_CTX + 512 * s.pred_mode;
         const uint32_t pm = s.pred_mode;
@@ -320,26 +324,55 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         uint8_t *dst = s.out + s.out_pos;
         Coder k = s.cur;
         Weights wh = s.c->w_hi, wl = s.c->w_lo;
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
-            const uint32_t byte_in = ENC ? src[i] : 0u;
-            __syncwarp();
-            const int h = mix_nibble<ENC>(k, g, writer, hi_base + ((size_t)(ctx * 256 + (ssb & mm & (~o1 & 0xffu)))) * 16, cmb + (size_t)ctx * 16,
-                                          wh, inc, lim, ch_inc, ch_lim, (int)(byte_in >> 4));
-            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
-            __syncwarp();
-            const int l = mix_nibble<ENC>(k, g, writer, lo_base + ((size_t)(ic * 256 + ib)) * 16, cmb + (size_t)(256 + h + 16 * ctx) * 16,
-                                          wl, inc, lim, cl_inc, cl_lim, (int)(byte_in & 0xf));
-            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
-            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);
-            if (g.store0) dst[i] = (uint8_t)cur;
-            uint32_t sel;
-            if (pm == 0) sel = cur & 0x3f;
-            else if (pm == 1) sel = cur >> 2;
-            else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
-            ctx = lcm[sel];
+        const uint32_t *const wbase = k.p;
+        const uint32_t wmax = k.left + 1;
+        uint32_t wi = 0;
+        if (!ENC) {   // eager refill for the duration of the loop (see the plain loop above)
+            coder_fill(k);
+            wi = (uint32_t)(k.p - wbase);
+            if (k.need_b) { k.b = (k.b << 32) | (uint64_t)wbase[wi]; wi = min(wi + 1, wmax); k.need_b = 0; }
         }
-        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += n; s.lit_left -= n;
+        uint32_t done = 0;
+        while (done < n) {
+            uint32_t m = n - done;
+            if (!ENC) {
+                if (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) {   // chunk restart, ans.rs:173-189
+                    if (wi + 5 <= wmax) { k.a = (uint64_t)wbase[wi] | ((uint64_t)wbase[wi + 1] << 32); k.b = (uint64_t)wbase[wi + 2] | ((uint64_t)wbase[wi + 3] << 32); wi += 4; }
+                    else { k.a = k.b = 0; wi = wmax; }
+                    k.sym_count = 0;
+                }
+                m = min(m, (NUM_SYMBOLS_BEFORE_FLUSH - k.sym_count) >> 1);
+                if (LPS == 16) m = min(m, __shfl_xor_sync(FULL, m, 16));
+                if (m == 0) break;
+            }
+            for (uint32_t i = 0; i < m; i++) {
+                const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
+                const uint32_t byte_in = ENC ? src[done + i] : 0u;
+                __syncwarp();
+                const int h = mix_nibble<ENC>(k, k.a, wbase, wi, wmax, g, writer, hi_tab + (ctx * 256u + (ssb & mm & (~o1 & 0xffu))) * 32u, cmb + ctx * 32u,
+                                              wh, inc, lim, ch_inc, ch_lim, (int)(byte_in >> 4));
+                const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
+                __syncwarp();
+                const int l = mix_nibble<ENC>(k, k.b, wbase, wi, wmax, g, writer, lo_tab + (ic * 256u + ib) * 32u, cmb + (256u + (uint32_t)h + 16u * ctx) * 32u,
+                                              wl, inc, lim, cl_inc, cl_lim, (int)(byte_in & 0xf));
+                const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+                l8 = (l8 >> 8) | ((unsigned long long)cur << 56);
+                if (g.store0) dst[done + i] = (uint8_t)cur;
+                uint32_t sel;
+                if (pm == 0) sel = cur & 0x3f;
+                else if (pm == 1) sel = cur >> 2;
+                else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+                ctx = lcm[sel];
+            }
+            done += m;
+            if (!ENC) k.sym_count += 2 * m;
+        }
+        if (!ENC) {
+            if (wi >= wmax) { k.underflow = 1; wi = wmax - 1; }
+            k.p = wbase + wi; k.left = wmax - 1 - wi;
+            k.need_a = (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) ? 8u : 0u; k.need_b = 0;
+        }
+        s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += done; s.lit_left -= done;
         s.c->w_hi = wh; s.c->w_lo = wl;
         enter_lit_nibble<ENC, true>(s, nx);
         return;
