@@ -183,3 +183,18 @@ def test_full_size_batch_roundtrip_property(engine, oracle):
     for i in pick:
         rc, ref = oracle.decode(enc[int(eoff[i]): int(eoff[i] + elen[i])].tobytes(), out_cap=65600)
         assert rc == 0 and ref == out[int(off[i]): int(off[i]) + 65536].tobytes()
+
+
+@pytest.mark.parametrize("p", [0.5, 0.9, 0.99])
+def test_entropy_sweep_one_mib_streams(engine, oracle, p):
+    # BASELINE configs[4] shape at reduced count: 1 MiB Bernoulli(p) streams (16 chunk restarts per coder, ans.rs:57,138)
+    import divans_b200
+    from divans_b200 import synth
+    blob, off, ln = synth.bernoulli_streams(6, 1 << 20, p, seed=int(p * 100))
+    raws = [blob[int(o):int(o + l)].tobytes() for o, l in zip(off, ln)]
+    streams = engine.encode(raws, divans_b200.encode_options())
+    assert streams[0] == oracle.encode_raw(raws[0]) and streams[5] == oracle.encode_raw(raws[5])
+    res = engine.decode(streams, [len(r) + 64 for r in raws])
+    assert all(st == 0 and out == r for (st, out), r in zip(res, raws))
+    rc, ref = oracle.decode(streams[3], out_cap=(1 << 20) + 64)
+    assert rc == 0 and ref == raws[3]
