@@ -4,16 +4,69 @@
 namespace dv {
 
 // ---------------------------------------------------------------------------------------------------------------
-// frame kernel: one thread per stream walks the 16-byte header and the mux record chain (mux.rs:384-444) to the
-// EOF marker, checks the trailer magic and the CRC32C of header..EOF marker (codec/decoder.rs:186-213).
+// framing pre-pass: frame kernel (header, record walk, trailer, CRC32C -- one warp per stream), payload scan, demux.
 // ---------------------------------------------------------------------------------------------------------------
 #if DV_LPS == 32
+// ---- CRC32C of one buffer by a whole warp: 32 contiguous segments, then a shuffle tree of CRC combinations ----
+// (crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B), polynomials in the reflected representation)
+constexpr uint32_t CRC32C_POLY = 0x82F63B78u;
+__device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {   // a * b mod P
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        p ^= (a & 0x80000000u) ? b : 0u;
+        a <<= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC32C_POLY : (b >> 1);
+    }
+    return p;
+}
+// x^(8 n) mod P by square-and-multiply over x2n[k] = x^(2^k) mod P
+__device__ __forceinline__ uint32_t gf_x8n(const uint32_t *x2n, uint32_t n) {
+    uint32_t p = 0x80000000u;   // x^0
+    for (uint32_t k = 3; n; n >>= 1, k++)
+        if (n & 1u) p = gf_mul(x2n[k & 31], p);
+    return p;
+}
+__device__ __forceinline__ uint32_t crc32c_bytes(const uint32_t (*tab)[256], const uint8_t *q, uint32_t n) {
+    uint32_t crc = 0xffffffffu, i = 0;
+    for (; i < n && (((uintptr_t)(q + i)) & 3); i++) crc = crc_step(tab[0], crc, q[i]);
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(q + i) ^ crc;
+        crc = tab[3][w & 0xff] ^ tab[2][(w >> 8) & 0xff] ^ tab[1][(w >> 16) & 0xff] ^ tab[0][w >> 24];
+    }
+    for (; i < n; i++) crc = crc_step(tab[0], crc, q[i]);
+    return ~crc;
+}
+__device__ uint32_t warp_crc32c(const uint32_t (*tab)[256], const uint32_t *x2n, const uint8_t *buf, uint32_t len, const int lane) {
+    const uint32_t seg = (len / 32u) & ~3u;
+    const uint32_t my_off = seg * (uint32_t)lane;
+    uint32_t my_len = lane == 31 ? len - 31u * seg : seg;
+    uint32_t crc = crc32c_bytes(tab, buf + my_off, my_len);
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t crc2 = __shfl_down_sync(FULL, crc, s), len2 = __shfl_down_sync(FULL, my_len, s);
+        if ((lane & (2 * s - 1)) == 0) {
+            crc = len2 ? (gf_mul(gf_x8n(x2n, len2), crc) ^ crc2) : crc;
+            my_len += len2;
+        }
+    }
+    return __shfl_sync(FULL, crc, 0);
+}
+
+// frame kernel: one WARP per stream.  Lane 0 walks the 16-byte header and the mux record chain (mux.rs:384-444) to the
+// EOF marker and checks the trailer magic; the warp checks the CRC32C of header..EOF marker (codec/decoder.rs:186-213).
 __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
     __shared__ uint32_t tab[4][256];   // slice-by-4 tables for the Castagnoli polynomial (reflected 0x82F63B78)
+    __shared__ uint32_t x2n[32];       // x^(2^k) mod P
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = i;
-        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ CRC32C_POLY : (c >> 1);
         tab[0][i] = c;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t v = 0x40000000u;      // x^1
+        x2n[0] = v;
+        for (int k = 1; k < 32; k++) { v = gf_mul(v, v); x2n[k] = v; }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -21,58 +74,56 @@ __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
         for (int t = 1; t < 4; t++) { c = tab[0][c & 0xff] ^ (c >> 8); tab[t][i] = c; }
     }
     __syncthreads();
-    uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (sidx >= p.n_streams) return;
     const uint8_t *in = p.in + p.in_off[sidx];
-    uint64_t n = p.in_len[sidx];
+    const uint64_t n = p.in_len[sidx];
     int32_t st = ST_OK;
     uint32_t body_end = 0, pay0 = 0, pay1 = 0;
-    if (n < 16) st = ST_NEED_INPUT;
-    else if (in[0] != 0xff || in[1] != 0xe5 || in[2] != 0x8c || in[3] != 0x9f) st = ST_FAIL;   // MAGIC_NUMBER, src/interface.rs:164
-    else if (in[5] < 10 || in[5] >= 25) st = ST_FAIL;                                             // BadWindowSize, divans_decompressor.rs:47-50
-    else {
-        uint64_t pos = 16;
-        for (;;) {
-            if (pos >= n) { st = ST_NEED_INPUT; break; }
-            uint32_t b = in[pos];
-            if (b == 0xff) {
-                if (pos + 3 > n) { st = ST_NEED_INPUT; break; }
-                if (in[pos + 1] != 0xfe || in[pos + 2] != 0xff) { st = ST_FAIL; break; }
-                body_end = (uint32_t)pos;
-                break;
-            }
-            uint64_t len, hdr;
-            if (b < 16) { if (pos + 3 > n) { st = ST_NEED_INPUT; break; } len = ((uint64_t)in[pos + 1] | ((uint64_t)in[pos + 2] << 8)) + 1; hdr = 3; }
-            else { uint32_t k = b >> 4; if (k > 3) { st = ST_FAIL; break; } len = 1024ull << (k << 1); hdr = 1; }
-            if (pos + hdr + len > n) { st = ST_NEED_INPUT; break; }
-            if (b & 1) pay1 += (uint32_t)len; else pay0 += (uint32_t)len;
-            pos += hdr + len;
-        }
-        if (st == ST_OK) {
-            uint64_t tr = (uint64_t)body_end + 3;
-            if (tr + 8 > n) st = ST_NEED_INPUT;
-            else {
-                if (in[tr + 4] != 'a' || in[tr + 5] != 'n' || in[tr + 6] != 's' || in[tr + 7] != '~') st = ST_FAIL;
-                if (st == ST_OK && !(p.flags & 3u)) {
-                    uint32_t crc = 0xffffffffu;
-                    uint64_t i = 0;
-                    for (; i < tr && (((uintptr_t)(in + i)) & 3); i++) crc = crc_step(tab[0], crc, in[i]);
-                    for (; i + 4 <= tr; i += 4) {
-                        uint32_t w = *reinterpret_cast<const uint32_t *>(in + i) ^ crc;
-                        crc = tab[3][w & 0xff] ^ tab[2][(w >> 8) & 0xff] ^ tab[1][(w >> 16) & 0xff] ^ tab[0][w >> 24];
-                    }
-                    for (; i < tr; i++) crc = crc_step(tab[0], crc, in[i]);
-                    crc = ~crc;
-                    uint32_t want = (uint32_t)in[tr] | ((uint32_t)in[tr + 1] << 8) | ((uint32_t)in[tr + 2] << 16) | ((uint32_t)in[tr + 3] << 24);
-                    if (crc != want) st = ST_FAIL;   // BadChecksum
+    if (lane == 0) {
+        if (n < 16) st = ST_NEED_INPUT;
+        else if (in[0] != 0xff || in[1] != 0xe5 || in[2] != 0x8c || in[3] != 0x9f) st = ST_FAIL;   // MAGIC_NUMBER, src/interface.rs:164
+        else if (in[5] < 10 || in[5] >= 25) st = ST_FAIL;                                             // BadWindowSize, divans_decompressor.rs:47-50
+        else {
+            uint64_t pos = 16;
+            for (;;) {
+                if (pos >= n) { st = ST_NEED_INPUT; break; }
+                uint32_t b = in[pos];
+                if (b == 0xff) {
+                    if (pos + 3 > n) { st = ST_NEED_INPUT; break; }
+                    if (in[pos + 1] != 0xfe || in[pos + 2] != 0xff) { st = ST_FAIL; break; }
+                    body_end = (uint32_t)pos;
+                    break;
                 }
+                uint64_t len, hdr;
+                if (b < 16) { if (pos + 3 > n) { st = ST_NEED_INPUT; break; } len = ((uint64_t)in[pos + 1] | ((uint64_t)in[pos + 2] << 8)) + 1; hdr = 3; }
+                else { uint32_t k = b >> 4; if (k > 3) { st = ST_FAIL; break; } len = 1024ull << (k << 1); hdr = 1; }
+                if (pos + hdr + len > n) { st = ST_NEED_INPUT; break; }
+                if (b & 1) pay1 += (uint32_t)len; else pay0 += (uint32_t)len;
+                pos += hdr + len;
+            }
+            if (st == ST_OK) {
+                const uint64_t tr = (uint64_t)body_end + 3;
+                if (tr + 8 > n) st = ST_NEED_INPUT;
+                else if (in[tr + 4] != 'a' || in[tr + 5] != 'n' || in[tr + 6] != 's' || in[tr + 7] != '~') st = ST_FAIL;
             }
         }
     }
-    p.frame[4 * sidx + 0] = st == ST_OK ? body_end : 0;
-    p.frame[4 * sidx + 1] = st == ST_OK ? pay0 : 0;
-    p.frame[4 * sidx + 2] = st == ST_OK ? pay1 : 0;
-    p.status[sidx] = st;
+    st = __shfl_sync(FULL, st, 0);
+    body_end = __shfl_sync(FULL, body_end, 0);
+    if (st == ST_OK && !(p.flags & 3u)) {
+        const uint32_t tr = body_end + 3;
+        const uint32_t crc = warp_crc32c(tab, x2n, in, tr, lane);
+        const uint32_t want = (uint32_t)in[tr] | ((uint32_t)in[tr + 1] << 8) | ((uint32_t)in[tr + 2] << 16) | ((uint32_t)in[tr + 3] << 24);
+        if (crc != want) st = ST_FAIL;   // BadChecksum
+    }
+    if (lane == 0) {
+        p.frame[4 * sidx + 0] = st == ST_OK ? body_end : 0;
+        p.frame[4 * sidx + 1] = st == ST_OK ? pay0 : 0;
+        p.frame[4 * sidx + 2] = st == ST_OK ? pay1 : 0;
+        p.status[sidx] = st;
+    }
 }
 
 // exclusive scan of the per-stream payload footprints -> frame[4i+3] = base of stream i's compacted payload (16-byte units)
@@ -230,7 +281,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodePara
 
 #if DV_LPS == 32
 void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st) {
-    uint32_t blocks = (p.n_streams + 127) / 128;
+    uint32_t blocks = (p.n_streams + 3) / 4;   // one warp per stream
     frame_kernel<<<blocks, 128, 0, st>>>(p);
     payload_scan_kernel<<<1, 1024, 0, st>>>(p.frame, p.n_streams);
     demux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p, payload);
