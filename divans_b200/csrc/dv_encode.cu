@@ -250,10 +250,16 @@ __device__ void vs_copy(const VStream &s, uint32_t pos, uint32_t len, uint8_t *d
 
 __global__ void __launch_bounds__(128) encode_mux_kernel(EncodeParams p) {
     __shared__ uint32_t tab[4][256];
+    __shared__ uint32_t x2n[32];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = i;
-        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ CRC32C_POLY : (c >> 1);
         tab[0][i] = c;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t v = 0x40000000u;      // x^1
+        x2n[0] = v;
+        for (int k = 1; k < 32; k++) { v = gf_mul(v, v); x2n[k] = v; }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -311,17 +317,9 @@ __global__ void __launch_bounds__(128) encode_mux_kernel(EncodeParams p) {
             if (lane == 0) { out[o] = 0xff; out[o + 1] = 0xfe; out[o + 2] = 0xff; }   // EOF marker, mux.rs:29
             __syncwarp();
             __threadfence_block();
+            const uint64_t tr = o + 3;
+            const uint32_t crc = warp_crc32c(tab, x2n, out, (uint32_t)tr, lane);   // codec/mod.rs:541-556
             if (lane == 0) {
-                const uint64_t tr = o + 3;
-                uint32_t crc = 0xffffffffu;
-                uint64_t i = 0;
-                for (; i < tr && (((uintptr_t)(out + i)) & 3); i++) crc = crc_step(tab[0], crc, out[i]);
-                for (; i + 4 <= tr; i += 4) {
-                    uint32_t w = *reinterpret_cast<const uint32_t *>(out + i) ^ crc;
-                    crc = tab[3][w & 0xff] ^ tab[2][(w >> 8) & 0xff] ^ tab[1][(w >> 16) & 0xff] ^ tab[0][w >> 24];
-                }
-                for (; i < tr; i++) crc = crc_step(tab[0], crc, out[i]);
-                crc = ~crc;
                 out[tr] = (uint8_t)crc; out[tr + 1] = (uint8_t)(crc >> 8); out[tr + 2] = (uint8_t)(crc >> 16); out[tr + 3] = (uint8_t)(crc >> 24);
                 out[tr + 4] = 'a'; out[tr + 5] = 'n'; out[tr + 6] = 's'; out[tr + 7] = '~';   // codec/mod.rs:541-556
                 p.out_len[v] = total;

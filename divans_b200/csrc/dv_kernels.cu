@@ -7,52 +7,6 @@ namespace dv {
 // framing pre-pass: frame kernel (header, record walk, trailer, CRC32C -- one warp per stream), payload scan, demux.
 // ---------------------------------------------------------------------------------------------------------------
 #if DV_LPS == 32
-// ---- CRC32C of one buffer by a whole warp: 32 contiguous segments, then a shuffle tree of CRC combinations ----
-// (crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B), polynomials in the reflected representation)
-constexpr uint32_t CRC32C_POLY = 0x82F63B78u;
-__device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {   // a * b mod P
-    uint32_t p = 0;
-#pragma unroll 4
-    for (int i = 0; i < 32; i++) {
-        p ^= (a & 0x80000000u) ? b : 0u;
-        a <<= 1;
-        b = (b & 1u) ? (b >> 1) ^ CRC32C_POLY : (b >> 1);
-    }
-    return p;
-}
-// x^(8 n) mod P by square-and-multiply over x2n[k] = x^(2^k) mod P
-__device__ __forceinline__ uint32_t gf_x8n(const uint32_t *x2n, uint32_t n) {
-    uint32_t p = 0x80000000u;   // x^0
-    for (uint32_t k = 3; n; n >>= 1, k++)
-        if (n & 1u) p = gf_mul(x2n[k & 31], p);
-    return p;
-}
-__device__ __forceinline__ uint32_t crc32c_bytes(const uint32_t (*tab)[256], const uint8_t *q, uint32_t n) {
-    uint32_t crc = 0xffffffffu, i = 0;
-    for (; i < n && (((uintptr_t)(q + i)) & 3); i++) crc = crc_step(tab[0], crc, q[i]);
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t *>(q + i) ^ crc;
-        crc = tab[3][w & 0xff] ^ tab[2][(w >> 8) & 0xff] ^ tab[1][(w >> 16) & 0xff] ^ tab[0][w >> 24];
-    }
-    for (; i < n; i++) crc = crc_step(tab[0], crc, q[i]);
-    return ~crc;
-}
-__device__ uint32_t warp_crc32c(const uint32_t (*tab)[256], const uint32_t *x2n, const uint8_t *buf, uint32_t len, const int lane) {
-    const uint32_t seg = (len / 32u) & ~3u;
-    const uint32_t my_off = seg * (uint32_t)lane;
-    uint32_t my_len = lane == 31 ? len - 31u * seg : seg;
-    uint32_t crc = crc32c_bytes(tab, buf + my_off, my_len);
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-        const uint32_t crc2 = __shfl_down_sync(FULL, crc, s), len2 = __shfl_down_sync(FULL, my_len, s);
-        if ((lane & (2 * s - 1)) == 0) {
-            crc = len2 ? (gf_mul(gf_x8n(x2n, len2), crc) ^ crc2) : crc;
-            my_len += len2;
-        }
-    }
-    return __shfl_sync(FULL, crc, 0);
-}
-
 // frame kernel: one WARP per stream.  Lane 0 walks the 16-byte header and the mux record chain (mux.rs:384-444) to the
 // EOF marker and checks the trailer magic; the warp checks the CRC32C of header..EOF marker (codec/decoder.rs:186-213).
 __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
