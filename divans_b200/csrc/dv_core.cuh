@@ -232,6 +232,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         uint8_t *dst = s.out + s.out_pos;
         Coder k = s.cur;
         const uint32_t src_last = s.lit_left - 1;                   // (lit_left >= 1 here)
+        const uint32_t pm_shift = pm == 1 ? 2u : 0u;
         // ---- decoder: switch the coder to EAGER refill for the duration of the loop ----
         // The reference refills a state right before it is used (ans.rs:428-442); the word order in the stream is the
         // order in which states were produced, so refilling a state as soon as it drops below 2^31 consumes the same
@@ -278,7 +279,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                 int h;
                 if (!ENC) {
                     const int rr = ((int)((uint32_t)k.a & 0x7fffu) * mh) >> 15;                    // probability/interface.rs:140
-                    h = __ffs((__ballot_sync(FULL, (g.l16 == 15) || (rr < ch)) >> g.shift) & 0xffffu) - 1;
+                    h = __ffs(__ballot_sync(FULL, (g.l16 == 15) || (rr < ch)) >> g.shift) - 1;   // bit 15 of the group is always set
                 } else h = (int)(byte_in >> 4);
                 const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
                 char *const pl = lo_tab + (ic * 256u + ib) * scale;
@@ -290,7 +291,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                     const int hi = __shfl_sync(FULL, cum, h, 16);
                     int lo = __shfl_sync(FULL, cum, (h - 1) & 15, 16);
                     if (h == 0) lo = 0;
-                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1) & 0xffffu;   // "major hax", probability/interface.rs:103-104
+                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
                     if (!ENC) {
                         const uint32_t t = ((uint32_t)k.a & 0x7fffu) - start;                      // 0 <= t < freq (the search put the offset in this bin)
                         uint64_t x = (uint64_t)freq * (k.a >> 15) + (uint64_t)t;                    // ans.rs:230-244
@@ -305,15 +306,13 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                 int l;
                 if (!ENC) {
                     const int rr = ((int)((uint32_t)k.b & 0x7fffu) * ml) >> 15;
-                    l = __ffs((__ballot_sync(FULL, (g.l16 == 15) || (rr < cl)) >> g.shift) & 0xffffu) - 1;
+                    l = __ffs(__ballot_sync(FULL, (g.l16 == 15) || (rr < cl)) >> g.shift) - 1;
                 } else l = (int)(byte_in & 0xf);
                 const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
                 l8 = (l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
                 if (g.store0) dst[done + i] = (uint8_t)cur;
-                uint32_t sel;                                         // get_prev_word_context, codec/literal.rs:87-117
-                if (pm == 0) sel = cur & 0x3f;
-                else if (pm == 1) sel = cur >> 2;
-                else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+                uint32_t sel = (cur >> pm_shift) & 0x3fu;             // get_prev_word_context, codec/literal.rs:87-117: LSB6 / MSB6
+                if (pm >= 2) sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));   // UTF8 / SIGN
                 ctx = lcm[sel];
                 ph = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * scale;
                 __syncwarp();
@@ -324,7 +323,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                     const int hi = __shfl_sync(FULL, cum, l, 16);
                     int lo = __shfl_sync(FULL, cum, (l - 1) & 15, 16);
                     if (l == 0) lo = 0;
-                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1) & 0xffffu;
+                    const uint32_t start = (uint32_t)(lo + 1), freq = (uint32_t)(hi - lo - 1);
                     if (!ENC) {
                         const uint32_t t = ((uint32_t)k.b & 0x7fffu) - start;
                         uint64_t x = (uint64_t)freq * (k.b >> 15) + (uint64_t)t;
