@@ -36,7 +36,7 @@ BATCH_SYMBOLS = [
     "divans_b200_create", "divans_b200_destroy", "divans_b200_last_error", "divans_b200_launch_count",
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
-    "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device",
+    "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device", "divans_b200_ir_to_cmds",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library():
     L.divans_b200_encode_cmds_batch_host.restype = ctypes.c_uint8
     L.divans_b200_encode_batch_device.argtypes = [vp, sz, vp, vp, vp, ctypes.c_uint64, vp, vp, vp, vp, vp, ctypes.POINTER(EncodeOptions), vp]
     L.divans_b200_encode_batch_device.restype = ctypes.c_uint8
+    L.divans_b200_ir_to_cmds.argtypes = [ctypes.c_char_p, sz, vp, sz, szp, ctypes.POINTER(ctypes.c_int32)]
+    L.divans_b200_ir_to_cmds.restype = ctypes.c_uint8
     # reference FFI
     L.divans_new_decompressor.restype = vp
     L.divans_new_serial_decompressor.restype = vp
@@ -124,6 +126,22 @@ def _u8(b):
     if isinstance(b, np.ndarray):
         return np.ascontiguousarray(b, dtype=np.uint8)
     return np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, np.uint8)
+
+
+def ir_to_cmds(text):
+    """Reference IR text (src/bin/divans.rs:191-483) -> (DVCL command-list blob, window size).  Host-side parser of the
+    C ABI (divans_b200_ir_to_cmds); feed the blob to ``Engine.encode(..., cmds=True)``."""
+    L = load_library()
+    t = text if isinstance(text, bytes) else text.encode()
+    need, win = ctypes.c_size_t(0), ctypes.c_int32(0)
+    rc = L.divans_b200_ir_to_cmds(t, len(t), None, 0, ctypes.byref(need), ctypes.byref(win))
+    if rc == DIVANS_FAILURE:
+        raise ValueError("IR parse failed")
+    out = np.zeros(need.value, np.uint8)
+    rc = L.divans_b200_ir_to_cmds(t, len(t), _ptr(out), out.size, ctypes.byref(need), ctypes.byref(win))
+    if rc != DIVANS_SUCCESS:
+        raise ValueError("IR parse failed")
+    return out.tobytes(), int(win.value)
 
 
 def encode_options(**kw):

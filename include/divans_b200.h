@@ -164,6 +164,11 @@ DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, 
                                                 const uint64_t *blob_len, uint8_t *out, const uint64_t *out_off,
                                                 const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
                                                 const divans_b200_encode_options *opts);
+/* IR text front-end (reference: src/bin/divans.rs:191-483, the textual IR that `divans -i` consumes): parse `ir_text` into a
+ * DVCL blob.  *blob_len receives the size of the blob; with out == NULL or out_cap too small the call returns
+ * DIVANS_NEEDS_MORE_OUTPUT.  *window_size (optional) receives the `window` line's value (0 if absent).  Host only. */
+DivansResult divans_b200_ir_to_cmds(const char *ir_text, size_t ir_len, uint8_t *out, size_t out_cap, size_t *blob_len,
+                                    int32_t *window_size);
 /*
  * command list blob ("DVCL", little endian) -- the binary form of the reference's IR (src/bin/divans.rs:191-483):
  *   u32 magic 0x4c435644, u32 version 1, u32 n_cmds, u32 n_predmodes, u32 n_literal_bytes, u32 window, u32[2] 0

@@ -139,3 +139,20 @@ def test_full_size_encode_decode_round_trip(engine, oracle):
     res = engine.decode(streams, [size + 64] * n)
     assert all(st == 0 for st, _ in res)
     assert all(out == raws[i] for i, (_, out) in enumerate(res))
+
+
+def test_ir_text_end_to_end(engine, oracle, text):
+    # reference IR text -> product parser (C ABI) -> GPU encoder == oracle encoder; GPU decode == oracle replay of the IR
+    import divans_b200
+    irs = [random_ir(oracle, 100 + seed, n_cmds=120, window=16, text=text) for seed in range(8)]
+    blobs = [divans_b200.ir_to_cmds(ir)[0] for ir in irs]
+    got = engine.encode(blobs, divans_b200.encode_options(window_size=16, dynamic_context_mixing=1), cmds=True)
+    raws = []
+    for i, ir in enumerate(irs):
+        c = oracle.Commands.from_ir(ir)
+        _check(got[i], c.encode(oracle.options(window_size=16, dynamic_context_mixing=1)), "IR %d" % i)
+        rc, raw = c.recode(16)
+        assert rc == 0
+        raws.append(raw)
+    res = engine.decode(got, [len(r) + 64 for r in raws])
+    assert all(st == 0 and out == r for (st, out), r in zip(res, raws))

@@ -124,3 +124,28 @@ def test_world_size_2_gloo_sharding():
     [p.join(60) for p in ps]
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 100
     assert res[0][3] == res[1][3] == 5050.0 and res[0][4] == res[1][4] == 2.0
+
+
+def test_ir_front_end_matches_oracle_parser(oracle):
+    """The product's C++ IR parser (divans_b200_ir_to_cmds) yields the same command-list blob as the oracle's parser --
+    which is pinned to the reference by replaying the reference's testdata/*.ir fixtures (tests/test_oracle_kat.py)."""
+    import divans_b200
+    from divans_b200 import synth
+    from irfuzz import random_ir
+    text = synth.text_corpus(1 << 16)
+    for seed in range(12):
+        ir = random_ir(oracle, seed, n_cmds=80, window=16 if seed % 2 else 22, text=text)
+        blob, win = divans_b200.ir_to_cmds(ir)
+        ref = oracle.Commands.from_ir(ir)
+        assert win == ref.window
+        assert blob == ref.serialize(), "seed %d" % seed
+    edge = "window 18 0 0 0\r\n\ninsert 0 \ncopy 0 from 5 ctx 3\nrndins 2 00ff\nltype 3\nltype 1 8\nctype 200\ndtype 2\n" \
+           "copy 7 from 2 ctx 0\ndict 5 word 4,9 6161 func 3 00 ctx 0\nprediction sign lcontextmap 1 2  3 dcontextmap 0 1 mixingvalues 4 4 stspeedinc 2 4 stspeedmax 1024 16384\n"
+    blob, win = divans_b200.ir_to_cmds(edge)
+    ref = oracle.Commands.from_ir(edge)
+    assert win == 18 and blob == ref.serialize()
+    for bad in ["bogus 1 2", "insert 3 00ff", "copy x from 1", "prediction nope", "insert 1 zz", "ltype 1 9", "dict 5 word 49 61 func 3"]:
+        with pytest.raises(ValueError):
+            divans_b200.ir_to_cmds(bad + "\n")
+        with pytest.raises(ValueError):
+            oracle.Commands.from_ir(bad + "\n")
