@@ -8,4 +8,6 @@ timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --skip-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -c 1 -o gpurun_out/${TAG}_decode python bench.py --streams 1024 --steps 1 --warmup 3 --skip-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:encode_model_kernel -c 1 -o gpurun_out/${TAG}_encode python bench.py --streams 1024 --steps 1 --warmup 3 --skip-cpu > gpurun_out/${TAG}_ncu_full_enc.log 2>&1; echo "ncu full enc rc=$?"
-ls -la gpurun_out | tail -12
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -c 1 -o gpurun_out/${TAG}_decode4096 python bench.py --streams 4096 --steps 1 --warmup 3 --skip-cpu > gpurun_out/${TAG}_ncu_full4096.log 2>&1; echo "ncu full 4096 rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
+ls -la gpurun_out | tail -14
