@@ -287,7 +287,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                 const int cl = ld_s16(pl + 2 * g.l16), ml = ld_s16(pl + 30);
                 // -- high nibble: finish
                 {
-                    const int cum = cdf_div(ch, mh);
+                    const int cum = cdf_div_pos(ch, mh);
                     const int hi = __shfl_sync(FULL, cum, h, 16);
                     int lo = __shfl_sync(FULL, cum, (h - 1) & 15, 16);
                     if (h == 0) lo = 0;
@@ -319,7 +319,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                 ch = ld_s16(ph + 2 * g.l16); mh = ld_s16(ph + 30);   // speculative on the last byte: a valid, initialised slab
                 // -- low nibble: finish
                 {
-                    const int cum = cdf_div(cl, ml);
+                    const int cum = cdf_div_pos(cl, ml);
                     const int hi = __shfl_sync(FULL, cum, l, 16);
                     int lo = __shfl_sync(FULL, cum, (l - 1) & 15, 16);
                     if (l == 0) lo = 0;

@@ -84,6 +84,20 @@ __device__ __forceinline__ int cdf_div(int c, int maxv) {
     return (int)qi;
 }
 
+// cdf_div for the literal fast loops: operands are known to be valid adaptive values (0 <= c <= max < 2^15), which lets
+// both conversions use the 32-bit ALU path (I2FP) instead of the 16-bit XU conversion.
+__device__ __forceinline__ int cdf_div_pos(int c, int maxv) {
+    const uint32_t d = (uint32_t)maxv;
+    const uint32_t n = (uint32_t)c << 15;
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(__uint2float_rz(d)));
+    uint32_t qi = __float2uint_rz(__uint2float_rz(n) * rc);
+    int32_t r = (int32_t)(n - qi * d);
+    if (r < 0) { qi--; r += (int32_t)d; }
+    if (r >= (int32_t)d) qi++;
+    return (int)qi;
+}
+
 // group-wide context handed around (all uniform except l16)
 struct Grp {
     unsigned mask;     // participating lanes of this group

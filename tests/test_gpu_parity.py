@@ -198,3 +198,29 @@ def test_entropy_sweep_one_mib_streams(engine, oracle, p):
     assert all(st == 0 and out == r for (st, out), r in zip(res, raws))
     rc, ref = oracle.decode(streams[3], out_cap=(1 << 20) + 64)
     assert rc == 0 and ref == raws[3]
+
+
+def test_corrupted_streams_without_crc_never_hang(engine, oracle, text):
+    # hostile input: records / payload bytes corrupted, CRC check skipped (reference: skip_crc) -> every stream comes back
+    # with a DivansResult code, the engine stays usable (codec/decoder.rs:204-210 relaxes only the checksum)
+    rng = np.random.default_rng(77)
+    import irfuzz
+    base = [oracle.Commands.from_ir(irfuzz.random_ir(oracle, seed, n_cmds=150, window=16, text=text)).encode(
+        oracle.options(window_size=16, dynamic_context_mixing=seed % 3)) for seed in range(12)]
+    base += [oracle.encode_raw(text[k * 9000: k * 9000 + 20000], oracle.options(window_size=10 + k)) for k in range(6)]
+    for _ in range(8):
+        streams = []
+        for s in base:
+            b = bytearray(s)
+            for _m in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(16, len(b) - 8))
+                if rng.random() < 0.5:
+                    b[pos] ^= 1 << int(rng.integers(0, 8))
+                else:
+                    ln = min(int(rng.integers(1, 64)), len(b) - 8 - pos)
+                    b[pos:pos + ln] = rng.integers(0, 256, ln).astype(np.uint8).tobytes()
+            streams.append(bytes(b))
+        res = engine.decode(streams, [1 << 20] * len(streams), flags=1)
+        assert all(st in (0, 1, 2, 3) for st, _ in res)
+    (st, out), = engine.decode([base[-1]], [1 << 20])
+    assert st == 0 and out == text[5 * 9000: 5 * 9000 + 20000]
