@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) encode_model_kernel(Enco
     s.c = reinterpret_cast<Cold *>(smem + group_in_block * SMEM_BYTES_PER_GROUP);
     s.tables = p.tables;
     s.state = S_IDLE;
-    s.c->in.cmds = nullptr; s.c->in.n_cmds = 0; s.c->in.pos = 0; s.c->in.pms = nullptr; s.c->in.lits = nullptr;
+    s.c->in.cmds = nullptr; s.c->in.n_cmds = 0; s.c->in.pos = 0; s.c->in.n_pms = 0; s.c->in.pms = nullptr; s.c->in.lits = nullptr;
     s.c->sidx = 0; s.c->raw_len = 0; s.c->lit_log_cap = p.lit_cap;
     s.out = p.replay + (uint64_t)slot * p.replay_stride; s.out_pos = 0;
     s.c->out_cap = p.replay_stride > 0xffffffffull ? 0xffffffffu : (uint32_t)p.replay_stride;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) encode_model_kernel(Enco
                     s.c->in.pos = 0;
                     if (p.raw_mode) {
                         if (blen > 0xffffffffull - 16) ok = false;
-                        s.c->in.cmds = nullptr; s.c->in.pms = p.pm_internal; s.c->in.lits = blob;
+                        s.c->in.cmds = nullptr; s.c->in.pms = p.pm_internal; s.c->in.n_pms = 1; s.c->in.lits = blob;
                         s.c->raw_len = (uint32_t)blen;
                         s.c->in.n_cmds = 1u + (uint32_t)((blen + s.c->ring_len - 1) >> p.window_size);
                     } else {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS) encode_model_kernel(Enco
                         else {
                             const uint64_t need = 32ull + 20ull * h[2] + (uint64_t)PM_RECORD_BYTES * h[3] + h[4];
                             if (need > blen) ok = false;
-                            s.c->in.cmds = h + 8; s.c->in.n_cmds = h[2];
+                            s.c->in.cmds = h + 8; s.c->in.n_cmds = h[2]; s.c->in.n_pms = h[3];
                             s.c->in.pms = blob + 32 + 20ull * h[2];
                             s.c->in.lits = s.c->in.pms + (uint64_t)PM_RECORD_BYTES * h[3];
                             s.c->raw_len = h[4];

@@ -63,7 +63,7 @@ constexpr int MI_DUMMY = 127;   // MISC slot idle groups "code" against while th
 // encoder input (DVCL blob, include/divans_b200.h)
 struct CmdIn {
     const uint32_t *cmds;    // 5 x u32 per command
-    uint32_t n_cmds, pos;
+    uint32_t n_cmds, pos, n_pms;
     const uint8_t *pms;      // prediction mode records (32 + 16384 + 1024 + 8192 each)
     const uint8_t *lits;     // literal pool
 };

@@ -18,6 +18,7 @@ __device__ __forceinline__ int load_cmd(St &s) {
     if (s.c->in.cmds) {
         const uint32_t *c = s.c->in.cmds + 5 * (size_t)pos;
         s.c->e0 = c[1]; s.c->e1 = c[2]; s.c->e2 = c[3]; s.c->e3 = c[4];
+        if (c[0] == 7u && c[1] >= s.c->in.n_pms) return 0;   // prediction-mode record out of range: not a command -> failure
         return (int)c[0];
     }
     if (pos == 0) { s.c->e0 = 0; s.c->e1 = 0; s.c->e2 = 0; s.c->e3 = 0; return 7; }

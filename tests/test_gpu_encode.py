@@ -156,3 +156,35 @@ def test_ir_text_end_to_end(engine, oracle, text):
         raws.append(raw)
     res = engine.decode(got, [len(r) + 64 for r in raws])
     assert all(st == 0 and out == r for (st, out), r in zip(res, raws))
+
+
+def test_corrupted_command_lists_never_hang(engine, oracle, text):
+    # hostile DVCL blobs (random words overwritten in the header / command records): a status per stream, no fault
+    rng = np.random.default_rng(5)
+    blobs = [np.frombuffer(oracle.Commands.from_ir(random_ir(oracle, 300 + s, n_cmds=100, window=16, text=text)).serialize(), np.uint8) for s in range(10)]
+    for _ in range(6):
+        bad = []
+        for b in blobs:
+            w = b.copy().view(np.uint32) if b.size % 4 == 0 else np.concatenate([b, np.zeros(4 - b.size % 4, np.uint8)]).view(np.uint32)
+            w = w.copy()
+            n_cmds = int(w[2])
+            for _m in range(int(rng.integers(1, 5))):
+                i = int(rng.integers(2, 8 + 5 * n_cmds))
+                w[i] = rng.integers(0, 1 << 32, dtype=np.uint64).astype(np.uint32) if rng.random() < 0.5 else np.uint32(rng.integers(0, 70000))
+            bad.append(w.view(np.uint8))
+        in_len = np.array([x.size for x in bad], np.uint64)
+        in_off = np.zeros(len(bad), np.uint64)
+        in_off[1:] = np.cumsum((in_len + np.uint64(15)) & ~np.uint64(15))[:-1]
+        blob = np.zeros(int(in_off[-1] + in_len[-1]) + 16, np.uint8)
+        for x, o in zip(bad, in_off):
+            blob[int(o):int(o) + x.size] = x
+        cap = np.full(len(bad), 1 << 20, np.uint64)
+        out_off = np.arange(len(bad), dtype=np.uint64) * np.uint64(1 << 20)
+        out = np.zeros(len(bad) << 20, np.uint8)
+        try:
+            ln, st = engine.encode_batch_host(blob, in_off, in_len, out, out_off, cap, None, cmds=True)
+            assert all(int(x) in (0, 1, 2, 3) for x in st)
+        except Exception as e:      # the host marshaller may refuse a batch whose header asks for absurd sizes
+            assert "too large" in str(e) or "encode_batch_host" in str(e)
+    good = engine.encode([blobs[0].tobytes()], None, cmds=True)
+    assert len(good[0]) > 24
