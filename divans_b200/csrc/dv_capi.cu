@@ -99,9 +99,7 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
               ck(ctx, cudaMemcpy(ctx->d_tables, dv_tables_blob, TB_TOTAL, cudaMemcpyHostToDevice), "cudaMemcpy(tables)") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_counter, 64), "cudaMalloc(counter)") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_nibbles, 64), "cudaMalloc(nibbles)") &&
-              ck(ctx, cudaMemset(ctx->d_nibbles, 0, 64), "cudaMemset") &&
-              ck(ctx, upload_ctx_lut32(dv_tables_blob + TB_CTX), "upload ctx lut") &&
-              ck(ctx, upload_ctx_lut16(dv_tables_blob + TB_CTX), "upload ctx lut");
+              ck(ctx, cudaMemset(ctx->d_nibbles, 0, 64), "cudaMemset");
     if (!ok) { delete ctx; return nullptr; }
     int per_sm = ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
     if (per_sm < 1) per_sm = 1;

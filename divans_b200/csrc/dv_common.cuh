@@ -125,7 +125,4 @@ struct EncodeParams {
 };
 constexpr uint32_t PM_RECORD_BYTES = 32 + 16384 + 1024 + 8192;
 
-// payload placement: stream i's two compacted byte streams live at payload + base(i): cmd first, lit at +align16(cmd bytes)
-__host__ __device__ inline uint64_t payload_base(uint64_t in_off, uint32_t i) { return (in_off + 48ull * i + 15ull) & ~15ull; }
-
 }  // namespace dv

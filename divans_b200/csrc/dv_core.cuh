@@ -82,36 +82,6 @@ __device__ __forceinline__ int nibble_core(St &s, const Next &nx, const G2 g, co
     return sym;
 }
 
-// Plain (non-mixing) nibble step split in three phases so that the literal fast path can software-pipeline it:
-//   lit_load   issue the two loads of the prior (element l16 and the maximum)
-//   lit_search refill the rANS state if needed and find the symbol (ballot)       -- on the critical path
-//   lit_finish exact start/freq, rANS state update, adaptive blend, store         -- off the critical path
-struct CdfRegs { int c, maxv; };
-__device__ __forceinline__ CdfRegs lit_load(const G2 g, const int16_t *cdf) { CdfRegs r; r.c = cdf[g.l16]; r.maxv = cdf[15]; return r; }
-template <bool ENC>
-__device__ __forceinline__ int lit_search(Coder &k, const G2 g, const CdfRegs r, const int sym_in) {
-    if (ENC) return sym_in;
-    coder_fill(k);
-    int off = (int)(k.a & 0x7fff);
-    int rr = (int)(short)((off * r.maxv) >> 15);                      // probability/interface.rs:140
-    bool pred = (g.l16 == 15) || (rr < r.c);
-    unsigned bal = __ballot_sync(FULL, pred);
-    return __ffs((bal >> g.shift) & 0xffffu) - 1;
-}
-template <bool ENC>
-__device__ __forceinline__ void lit_finish(Coder &k, const G2 g, const bool writer, int16_t *cdf, const CdfRegs r, const int sym, const int inc, const int lim) {
-    int cum = cdf_div(r.c, r.maxv);
-    int hi = __shfl_sync(FULL, cum, sym, 16);
-    int lo = __shfl_sync(FULL, cum, (sym - 1) & 15, 16);
-    if (sym == 0) lo = 0;
-    int start = (int)(short)(lo + 1), freq = (int)(short)(hi - lo - 1);   // "major hax", probability/interface.rs:103-104
-    if (!ENC) coder_advance(k, start, freq);
-    else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
-    int c2 = (int)(short)(r.c + ((g.l16 >= sym) ? inc : 0));
-    if ((int)(short)(r.maxv + inc) >= lim) { int t = (int)(short)(c2 + g.l16 + 1); c2 = (int)(short)(t - (t >> 2)); }
-    if (writer) cdf[g.l16] = (int16_t)c2;
-}
-
 // ---- CRC32C of one buffer by a whole warp: 32 contiguous segments, then a shuffle tree of CRC combinations ----
 // (crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B), polynomials in the reflected representation)
 constexpr uint32_t CRC32C_POLY = 0x82F63B78u;

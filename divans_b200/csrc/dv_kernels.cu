@@ -240,10 +240,6 @@ void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st) {
     payload_scan_kernel<<<1, 1024, 0, st>>>(p.frame, p.n_streams);
     demux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p, payload);
 }
-// each translation unit has its own copy of the __constant__ LUT: upload to both
-cudaError_t upload_ctx_lut32(const uint8_t *host2048) { return cudaMemcpyToSymbol(c_ctx_lut, host2048, 2048); }
-#else
-cudaError_t upload_ctx_lut16(const uint8_t *host2048) { return cudaMemcpyToSymbol(c_ctx_lut, host2048, 2048); }
 #endif
 #ifndef DV_LPS
 #error "compile with -DDV_LPS=16 or 32 (one translation unit per instantiation keeps ptxas time in check)"

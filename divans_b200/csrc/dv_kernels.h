@@ -8,8 +8,6 @@ constexpr int DECODE_BLOCK_THREADS = 64;
 void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st);   // frame + payload scan + demux (3 launches)
 void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
-cudaError_t upload_ctx_lut32(const uint8_t *host2048);
-cudaError_t upload_ctx_lut16(const uint8_t *host2048);
 int decode_max_blocks_per_sm32();
 int decode_max_blocks_per_sm16();
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes

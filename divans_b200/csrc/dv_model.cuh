@@ -18,7 +18,6 @@
 
 namespace dv {
 
-__constant__ uint8_t c_ctx_lut[2048];   // mode*512 + {lut0[256], lut1[256]}   (codec/interface.rs:199-238)
 
 struct Speed2 { int inc, lim; };
 
