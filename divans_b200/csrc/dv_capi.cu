@@ -265,7 +265,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     if (!grow(ctx, &ctx->d_sf, &ctx->sf_cap, n * ((size_t)cmd_cap + lit_cap))) return DIVANS_FAILURE;
     if (!grow(ctx, &ctx->d_replay, &ctx->replay_cap, slots * (size_t)replay_stride)) return DIVANS_FAILURE;
     // small per-stream scratch: counts [2n] | dummy [slots] | chunk_w [n*max_chunks] | chunk_state [16*n*max_chunks]
-    size_t words = 2 * n + slots + n * (size_t)max_chunks + 4 * n * (size_t)max_chunks + 16;
+    size_t words = 2 * n + slots + n * (size_t)max_chunks + 4 * n * (size_t)max_chunks + 16 + 2 * n * (size_t)max_chunks * (NUM_SYMBOLS_BEFORE_FLUSH / 64);
     if (!grow(ctx, &ctx->d_enc_scratch, &ctx->enc_scratch_cap, words)) return DIVANS_FAILURE;
     if (!ctx->d_pm_internal) CK(cudaMalloc((void **)&ctx->d_pm_internal, PM_RECORD_BYTES));
     if (!ctx->d_rcp15) { CK(cudaMalloc((void **)&ctx->d_rcp15, 32768 * sizeof(uint64_t))); launch_rcp15_init(ctx->d_rcp15, st); ctx->launches += 1; }
@@ -290,6 +290,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     ep.chunk_w = w; w += n * (size_t)max_chunks;
     w = reinterpret_cast<uint32_t *>(((uintptr_t)w + 15) & ~(uintptr_t)15);
     ep.chunk_state = reinterpret_cast<uint8_t *>(w);
+    ep.emit_bits = w + 4 * n * (size_t)max_chunks;
     ep.rcp15 = ctx->d_rcp15;
     ep.replay = ctx->d_replay; ep.replay_stride = replay_stride;
     ep.max_chunks = max_chunks; ep.cmd_chunks = cmd_chunks;
@@ -306,7 +307,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     launch_encode_flush_mux(ep, st);
     CK(cudaEventRecord(ctx->ev1, st));
     ctx->main_end_is_evm1 = true;
-    ctx->launches += 3;
+    ctx->launches += 4;
     CK(cudaGetLastError());
     return DIVANS_SUCCESS;
 }

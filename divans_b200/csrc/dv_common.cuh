@@ -117,6 +117,7 @@ struct EncodeParams {
     uint32_t *chunk_w;            // per chunk: first u32 entry of the chunk's renormalisation words (in place in the log)
     uint8_t *chunk_state;         // per chunk: the 16 bytes of final states that precede them
     const uint64_t *rcp15;        // floor((2^64 - 1) / f) for f < 32768 (reverse rANS pass)
+    uint32_t *emit_bits;          // per (chunk, state): 1024 words, bit i = the state's i-th symbol from the end emitted a word
     uint8_t *out; const uint64_t *out_off, *out_cap; uint64_t *out_len;
     int32_t *status;
     // options (reference: DivansCompressorOptions, src/interface.rs:444-484)

@@ -5,9 +5,9 @@
 //   1. encode_model_kernel  the lock-step engine (dv_engine.cuh) run with ENC=true: walks the command list, adapts
 //                           the priors exactly as the decoder will, and logs one (start | freq << 16) word per nibble
 //                           into the stream's command / literal log.
-//   2. encode_flush_kernel  one thread per 65536-symbol chunk runs the rANS recurrence last symbol -> first symbol
-//                           (ans.rs:302-378).  A symbol emits at most one 32-bit word, so the words are stacked IN
-//                           PLACE at the top of the chunk's own log region.
+//   2. encode_flush_kernel  one thread per (65536-symbol chunk, rANS state) runs the recurrence last symbol -> first
+//                           symbol (ans.rs:302-378); encode_pack_kernel then stacks the renormalisation words in
+//                           symbol order IN PLACE at the top of the chunk's own log region (<= one word per symbol).
 //   3. encode_mux_kernel    one warp per stream: header, the record chain of Mux::serialize_close with everything
 //                           still buffered (mux.rs:478-561), EOF marker, CRC32C and trailer (codec/mod.rs:493-560).
 #include "dv_core.cuh"
@@ -143,80 +143,116 @@ __device__ __forceinline__ uint64_t div_by_u15(uint64_t x, uint32_t f, uint64_t 
     return q;
 }
 
+// thread <-> (stream, chunk record, rANS state).  The two interleaved states of a chunk are independent recurrences
+// (symbol j counted from the end belongs to state j & 1, ans.rs:350-352); only the ORDER of their renormalisation words
+// in the byte stack couples them.  So each state runs in its own thread, leaves a word in place of the log entry that
+// produced it plus one bit in its emission bitmap, and encode_pack_kernel stacks the words in symbol order afterwards.
 __global__ void __launch_bounds__(128) encode_flush_kernel(EncodeParams p) {
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t tt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = tt >> 1;
+    const uint32_t parity = (uint32_t)tt & 1u;
     const uint32_t v = (uint32_t)(t / p.max_chunks), j = (uint32_t)(t % p.max_chunks);
     if (v >= p.n_streams) return;
     const bool lit = j >= p.cmd_chunks;
     const uint32_t cj = lit ? j - p.cmd_chunks : j;
     const uint32_t count = p.sf_counts[2 * v + (lit ? 1 : 0)];
     const uint32_t first = cj * NUM_SYMBOLS_BEFORE_FLUSH;
-    if (first >= count) { p.chunk_w[t] = 0xffffffffu; return; }
+    if (first >= count) { if (!parity) p.chunk_w[t] = 0xffffffffu; return; }
     const uint32_t last = min(count, first + NUM_SYMBOLS_BEFORE_FLUSH);
+    const uint32_t cnt = last - first;
     uint32_t *sf = p.sf + (uint64_t)v * (p.cmd_cap + p.lit_cap) + (lit ? p.cmd_cap : 0);
-    uint64_t sa = 1ull << 31, sb = 1ull << 31;
-    uint32_t w = last;
-    // one step of ans.rs:330-352 for state `st` and log entry `e`; a symbol emits at most one word and w > k always,
-    // so the renormalisation words are stacked in place at the top of the chunk's own log region
-#define DV_RANS_PUT(st, e, Mv)                                                                                   \
+    uint32_t *bits = p.emit_bits + tt * (NUM_SYMBOLS_BEFORE_FLUSH / 64);
+    const uint32_t mine = (cnt + 1 - parity) >> 1;          // symbols of this state
+    uint64_t st = 1ull << 31;
+    uint32_t acc = 0;
+    // one step of ans.rs:330-352; a symbol emits at most one 32-bit word
+#define DV_RANS_PUT(e, Mv, idx, slot)                                                                          \
     {                                                                                                          \
         const uint32_t f_ = ((e) >> 16) & 0x7fffu;     /* freq is 1..32767 for every prior the model can reach */ \
         const uint64_t start_ = (uint64_t)(int64_t)(short)((e) & 0xffffu);                                     \
-        if ((st) >= ((uint64_t)f_ << 48)) { sf[--w] = (uint32_t)(st); (st) >>= 32; }                           \
+        if ((uint32_t)(st >> 32) >= (f_ << 16)) { sf[slot] = (uint32_t)st; st >>= 32; acc |= 1u << ((idx) & 31); }  \
         uint32_t rem_;                                                                                         \
-        const uint64_t q_ = div_by_u15((st), f_ ? f_ : 1u, (Mv), rem_);                                        \
-        (st) = (q_ << 15) + rem_ + start_;                                                                     \
+        const uint64_t q_ = div_by_u15(st, f_ ? f_ : 1u, (Mv), rem_);                                          \
+        st = (q_ << 15) + rem_ + start_;                                                                       \
+        if (((idx) & 31) == 31) { bits[(idx) >> 5] = acc; acc = 0; }                                           \
     }
-    // Symbols are taken last -> first; symbol j (counted from the end) belongs to state a when j is even, to b when odd
-    // (the rotation of ans.rs:350-352).  The log entries and their reciprocals are fetched one block of 8 symbols ahead
-    // of the arithmetic, so the only serial chain left is state -> state.
+    // log entries and reciprocals are fetched one block of 8 symbols ahead of the arithmetic
     constexpr int BLK = 8;
-    const uint32_t cnt = last - first;
-    const uint32_t n_blk = cnt / BLK;
+    const uint32_t n_blk = mine / BLK;
     uint32_t e[BLK]; uint64_t M[BLK];
-    uint32_t k = last;
+    uint32_t k = last - 1 - parity;      // entry of this state's next symbol (valid while i < mine)
     if (n_blk) {
 #pragma unroll
-        for (int i = 0; i < BLK; i++) e[i] = sf[k - 1 - i];
+        for (int i = 0; i < BLK; i++) e[i] = sf[k - 2 * i];
 #pragma unroll
         for (int i = 0; i < BLK; i++) { const uint32_t f_ = (e[i] >> 16) & 0x7fffu; M[i] = __ldg(p.rcp15 + (f_ ? f_ : 1u)); }
     }
+    uint32_t idx = 0;
     for (uint32_t blk = 0; blk < n_blk; blk++) {
         uint32_t en[BLK]; uint64_t Mn[BLK];
         const bool more = blk + 1 < n_blk;
         if (more) {
 #pragma unroll
-            for (int i = 0; i < BLK; i++) en[i] = sf[k - BLK - 1 - i];
+            for (int i = 0; i < BLK; i++) en[i] = sf[k - 2 * BLK - 2 * i];
 #pragma unroll
             for (int i = 0; i < BLK; i++) { const uint32_t f_ = (en[i] >> 16) & 0x7fffu; Mn[i] = __ldg(p.rcp15 + (f_ ? f_ : 1u)); }
         }
 #pragma unroll
-        for (int i = 0; i < BLK; i += 2) {
-            DV_RANS_PUT(sa, e[i], M[i])
-            DV_RANS_PUT(sb, e[i + 1], M[i + 1])
-        }
-        k -= BLK;
+        for (int i = 0; i < BLK; i++) DV_RANS_PUT(e[i], M[i], idx + i, k - 2 * i)
+        k -= 2 * BLK; idx += BLK;
         if (more) {
 #pragma unroll
             for (int i = 0; i < BLK; i++) { e[i] = en[i]; M[i] = Mn[i]; }
         }
     }
-    {   // tail: fewer than BLK symbols
-        bool use_a = true;
-        for (; k > first; k--) {
-            const uint32_t e1 = sf[k - 1];
-            const uint32_t f1 = (e1 >> 16) & 0x7fffu;
-            const uint64_t M1 = __ldg(p.rcp15 + (f1 ? f1 : 1u));
-            if (use_a) { DV_RANS_PUT(sa, e1, M1) } else { DV_RANS_PUT(sb, e1, M1) }
-            use_a = !use_a;
-        }
-        if (cnt & 1) { const uint64_t tmp = sa; sa = sb; sb = tmp; }   // odd count: the roles end up swapped
+    for (; idx < mine; idx++, k -= 2) {
+        const uint32_t e1 = sf[k];
+        const uint32_t f1 = (e1 >> 16) & 0x7fffu;
+        const uint64_t M1 = __ldg(p.rcp15 + (f1 ? f1 : 1u));
+        DV_RANS_PUT(e1, M1, idx, k)
     }
 #undef DV_RANS_PUT
-    { const uint64_t tmp = sa; sa = sb; sb = tmp; }
+    if (mine & 31) bits[mine >> 5] = acc;
+    // final states: after cnt rotations (and the closing swap of ans.rs:354-360) state 0 lands in slot (cnt even ? 1 : 0)
     uint64_t *cs = reinterpret_cast<uint64_t *>(p.chunk_state + 16 * t);
-    cs[0] = sa; cs[1] = sb;
-    p.chunk_w[t] = w;
+    cs[((cnt & 1u) ? parity : (parity ^ 1u))] = st;
+}
+
+// one warp per chunk record: stack the renormalisation words in symbol order (last symbol first) at the top of the
+// chunk's own log region.  Pair i = symbols 2i (state 0) and 2i+1 (state 1) counted from the end; the two emission
+// bitmaps are the ballots, so destinations are prefix popcounts.
+__global__ void __launch_bounds__(128) encode_pack_kernel(EncodeParams p) {
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t v = (uint32_t)(t / p.max_chunks), j = (uint32_t)(t % p.max_chunks);
+    if (v >= p.n_streams) return;
+    const bool lit = j >= p.cmd_chunks;
+    const uint32_t cj = lit ? j - p.cmd_chunks : j;
+    const uint32_t count = p.sf_counts[2 * v + (lit ? 1 : 0)];
+    const uint32_t first = cj * NUM_SYMBOLS_BEFORE_FLUSH;
+    if (first >= count) return;
+    const uint32_t last = min(count, first + NUM_SYMBOLS_BEFORE_FLUSH);
+    const uint32_t cnt = last - first;
+    uint32_t *sf = p.sf + (uint64_t)v * (p.cmd_cap + p.lit_cap) + (lit ? p.cmd_cap : 0);
+    const uint32_t *bits0 = p.emit_bits + (2 * t) * (NUM_SYMBOLS_BEFORE_FLUSH / 64), *bits1 = bits0 + NUM_SYMBOLS_BEFORE_FLUSH / 64;
+    const uint32_t n0 = (cnt + 1) >> 1, n1 = cnt >> 1;
+    uint32_t w = last;
+    const uint32_t below = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < n0; base += 32) {
+        uint32_t m0 = bits0[base >> 5], m1 = base < n1 ? bits1[base >> 5] : 0u;
+        if (n0 - base < 32) m0 &= (1u << (n0 - base)) - 1u;
+        if (base < n1 && n1 - base < 32) m1 &= (1u << (n1 - base)) - 1u;
+        const uint32_t i = base + lane;
+        const bool e0 = (m0 >> lane) & 1u, e1 = (m1 >> lane) & 1u;
+        const uint32_t w0 = e0 ? sf[last - 1 - 2 * i] : 0u, w1 = e1 ? sf[last - 2 - 2 * i] : 0u;
+        __syncwarp();
+        const uint32_t before = __popc(m0 & below) + __popc(m1 & below);
+        if (e0) sf[w - 1 - before] = w0;
+        if (e1) sf[w - 1 - before - (e0 ? 1u : 0u)] = w1;
+        w -= __popc(m0) + __popc(m1);
+        __syncwarp();
+    }
+    if (lane == 0) p.chunk_w[t] = w;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -340,7 +376,8 @@ __global__ void rcp15_init_kernel(uint64_t *tab) {
 void launch_rcp15_init(uint64_t *tab, cudaStream_t st) { rcp15_init_kernel<<<32768 / 256, 256, 0, st>>>(tab); }
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st) {
     const uint64_t items = (uint64_t)p.n_streams * p.max_chunks;
-    encode_flush_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(p);
+    encode_flush_kernel<<<(unsigned)((2 * items + 127) / 128), 128, 0, st>>>(p);
+    encode_pack_kernel<<<(unsigned)((items * 32 + 127) / 128), 128, 0, st>>>(p);
     encode_mux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p);
 }
 int encode_max_blocks_per_sm() {
