@@ -159,14 +159,47 @@ __device__ __forceinline__ void weights_update(Weights &w, int f_cm, int f_nb, i
     w.norm = (int)(unsigned short)(q << 7);
 }
 
+// RECIPROCAL8[d] = 1 + 2^24 / d (d = 1..255; the reference's div_lut.rs table for compute_normalized_weight), [0] = 0
+__constant__ uint32_t c_recip8[256] = {
+    0u, 16777217u, 8388609u, 5592406u, 4194305u, 3355444u, 2796203u, 2396746u,
+    2097153u, 1864136u, 1677722u, 1525202u, 1398102u, 1290556u, 1198373u, 1118482u,
+    1048577u, 986896u, 932068u, 883012u, 838861u, 798916u, 762601u, 729445u,
+    699051u, 671089u, 645278u, 621379u, 599187u, 578525u, 559241u, 541201u,
+    524289u, 508401u, 493448u, 479350u, 466034u, 453439u, 441506u, 430186u,
+    419431u, 409201u, 399458u, 390168u, 381301u, 372828u, 364723u, 356963u,
+    349526u, 342393u, 335545u, 328966u, 322639u, 316552u, 310690u, 305041u,
+    299594u, 294338u, 289263u, 284360u, 279621u, 275037u, 270601u, 266306u,
+    262145u, 258112u, 254201u, 250407u, 246724u, 243149u, 239675u, 236299u,
+    233017u, 229825u, 226720u, 223697u, 220753u, 217886u, 215093u, 212370u,
+    209716u, 207127u, 204601u, 202136u, 199729u, 197380u, 195084u, 192842u,
+    190651u, 188509u, 186414u, 184366u, 182362u, 180401u, 178482u, 176603u,
+    174763u, 172961u, 171197u, 169467u, 167773u, 166112u, 164483u, 162886u,
+    161320u, 159784u, 158276u, 156797u, 155345u, 153920u, 152521u, 151147u,
+    149797u, 148471u, 147169u, 145889u, 144632u, 143396u, 142180u, 140986u,
+    139811u, 138655u, 137519u, 136401u, 135301u, 134218u, 133153u, 132105u,
+    131073u, 130056u, 129056u, 128071u, 127101u, 126145u, 125204u, 124276u,
+    123362u, 122462u, 121575u, 120700u, 119838u, 118988u, 118150u, 117324u,
+    116509u, 115705u, 114913u, 114131u, 113360u, 112599u, 111849u, 111108u,
+    110377u, 109656u, 108943u, 108241u, 107547u, 106862u, 106185u, 105518u,
+    104858u, 104207u, 103564u, 102928u, 102301u, 101681u, 101068u, 100463u,
+    99865u, 99274u, 98690u, 98113u, 97542u, 96979u, 96421u, 95870u,
+    95326u, 94787u, 94255u, 93728u, 93207u, 92692u, 92183u, 91679u,
+    91181u, 90688u, 90201u, 89718u, 89241u, 88769u, 88302u, 87839u,
+    87382u, 86929u, 86481u, 86038u, 85599u, 85164u, 84734u, 84308u,
+    83887u, 83469u, 83056u, 82647u, 82242u, 81841u, 81443u, 81050u,
+    80660u, 80274u, 79892u, 79513u, 79138u, 78767u, 78399u, 78034u,
+    77673u, 77315u, 76960u, 76609u, 76261u, 75916u, 75574u, 75235u,
+    74899u, 74566u, 74236u, 73909u, 73585u, 73263u, 72945u, 72629u,
+    72316u, 72006u, 71698u, 71393u, 71090u, 70790u, 70493u, 70198u,
+    69906u, 69616u, 69328u, 69043u, 68760u, 68479u, 68201u, 67924u,
+    67651u, 67379u, 67109u, 66842u, 66577u, 66314u, 66053u, 65794u,
+};
+
 // 32-bit restatement of weights_update for the literal fast path.  Identical results whenever the coded frequencies
 // are in 1..32767 (always true for streams an encoder can produce): efficacy = 2^15 * (prob - p1) and
 // prod = p0 * efficacy, so prod >> lg is (p0 * (prob - p1)) shifted by (15 - lg) -- no 64-bit arithmetic needed.
-__device__ __forceinline__ int weights_new32(int prob, int p1, int wi) {
-    const int p0 = (1 << 15) - p1;
+__device__ __forceinline__ int weights_new32(int prob, int p1, int p0, int lg, int wi) {
     const int t = p0 * (prob - p1);
-    const unsigned geo = (unsigned)(p1 * p0);
-    const int lg = geo ? 32 - __clz((int)geo) : 0;
     const int adj = lg <= 15 ? (int)((unsigned)t << (15 - lg)) : (t >> (lg - 15));
     const int nw = (int)((unsigned)wi + (unsigned)adj);
     return nw > 1 ? nw : 1;
@@ -176,13 +209,16 @@ __device__ __forceinline__ void weights_update32(Weights &w, int f_cm, int f_nb,
         int ilog = 32 - min(__clz(w.w0), __clz(w.w1));
         if (ilog >= 24) { w.w0 >>= ilog - 24; w.w1 >>= ilog - 24; }
     }
-    const int n0 = weights_new32(f_cm, weighted, w.w0);
-    const int n1 = weights_new32(f_nb, weighted, w.w1);
+    const int p0 = (1 << 15) - weighted;
+    const unsigned geo = (unsigned)(weighted * p0);
+    const int lg = geo ? 32 - __clz((int)geo) : 0;
+    const int n0 = weights_new32(f_cm, weighted, p0, lg, w.w0);
+    const int n1 = weights_new32(f_nb, weighted, p0, lg, w.w1);
     w.w0 = n0; w.w1 = n1;
     const unsigned total = (unsigned)n0 + (unsigned)n1;       // compute_normalized_weight, :54-62 (total < 2^32)
     const int shift = max(24 - __clz((int)total), 0);
     const unsigned d = (total >> shift) & 0xffu;
-    const int recip = d ? 1 + cdf_div(512, (int)d) : 0;       // RECIPROCAL8[d] = 1 + 2^24 / d (div_lut.rs)
+    const int recip = (int)c_recip8[d];
     const unsigned num = ((unsigned)(n0 >> shift) << 8) & 0xffffu;
     const int q = (int)(short)(((unsigned long long)(unsigned)recip * num) >> 24);
     w.norm = (int)(unsigned short)(q << 7);
