@@ -132,28 +132,37 @@ static __device__ uint32_t warp_crc32c(const uint32_t (*tab)[256], const uint32_
 __device__ __forceinline__ int ld_s16(const char *p) { int v; asm volatile("ld.global.s16 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 // One literal nibble coded against the mix of two priors (dynamic context mixing >= 2, codec/literal.rs:219-259):
 // `nb` = the stride prior, `cm` = the context-map prior, weights `w` (model_weights[high nibble ? 1 : 0]).
+// Three phases so that the loop can issue the loads of the next nibble before the long finish of the current one.
+struct MixVals { int c, maxv, cc, mc; };
+__device__ __forceinline__ MixVals mix_load(const G2 g, const char *nb, const char *cm) {
+    MixVals v; v.c = ld_s16(nb + 2 * g.l16); v.maxv = ld_s16(nb + 30); v.cc = ld_s16(cm + 2 * g.l16); v.mc = ld_s16(cm + 30); return v;
+}
+struct MixSym { int sym, ca, ma; };
 template <bool ENC>
-__device__ __forceinline__ int mix_nibble(Coder &k, uint64_t &st, const uint32_t *const wbase, uint32_t &wi, const uint32_t wmax,
-                                          const G2 g, const bool writer, char *nb, char *cm, Weights &w,
-                                          const int nb_inc, const int nb_lim, const int cm_inc, const int cm_lim, const int sym_in) {
-    const int c = ld_s16(nb + 2 * g.l16), maxv = ld_s16(nb + 30), cc = ld_s16(cm + 2 * g.l16), mc = ld_s16(cm + 30);
-    const int prod = mc * maxv;
+__device__ __forceinline__ MixSym mix_search(const uint64_t st, const G2 g, const MixVals v, const Weights &w, const int sym_in) {
+    const int prod = v.mc * v.maxv;
     int lz = prod == 0 ? 32 : __clz(prod); if (lz > 17) lz = 17;
     const int shift = 17 - lz;
     const int mixr = w.norm, inv = (1 << 15) - mixr;
-    const int rs = (cc * maxv) >> shift, ro = (c * mc) >> shift;
-    const int ca = (int)(short)((int)((unsigned)rs * (unsigned)mixr + (unsigned)ro * (unsigned)inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
-    const int ma = __shfl_sync(FULL, ca, 15, 16);
-    int sym;
+    const int rs = (v.cc * v.maxv) >> shift, ro = (v.c * v.mc) >> shift;
+    MixSym r;
+    r.ca = (int)(short)((int)((unsigned)rs * (unsigned)mixr + (unsigned)ro * (unsigned)inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
+    r.ma = __shfl_sync(FULL, r.ca, 15, 16);
     if (!ENC) {
-        const int r = (int)(short)(((int)((uint32_t)st & 0x7fffu) * ma) >> 15);
-        const bool pred = (g.l16 == 15) || (r < ca);
-        const unsigned bal = __ballot_sync(FULL, pred);
-        sym = __ffs((bal >> g.shift) & 0xffffu) - 1;
-    } else sym = sym_in;
+        const int q = (int)(short)(((int)((uint32_t)st & 0x7fffu) * r.ma) >> 15);
+        const bool pred = (g.l16 == 15) || (q < r.ca);
+        r.sym = __ffs(__ballot_sync(FULL, pred) >> g.shift) - 1;
+    } else r.sym = sym_in;
+    return r;
+}
+template <bool ENC>
+__device__ __forceinline__ void mix_finish(Coder &k, uint64_t &st, const uint32_t *const wbase, uint32_t &wi, const uint32_t wmax,
+                                           const G2 g, const bool writer, char *nb, char *cm, const MixVals v, const MixSym ms, Weights &w,
+                                           const int nb_inc, const int nb_lim, const int cm_inc, const int cm_lim) {
+    const int sym = ms.sym;
     // cumulative values of the three CDFs at sym and sym-1: two registers, four shuffles
-    const int cum_a = cdf_div(ca, ma);
-    const int cum_pn = cdf_div(cc, mc) | (cdf_div(c, maxv) << 16);
+    const int cum_a = cdf_div(ms.ca, ms.ma);
+    const int cum_pn = cdf_div(v.cc, v.mc) | (cdf_div(v.c, v.maxv) << 16);
     const int prev = (sym - 1) & 15;
     const int hi_a = __shfl_sync(FULL, cum_a, sym, 16), hi_pn = __shfl_sync(FULL, cum_pn, sym, 16);
     int lo_a = __shfl_sync(FULL, cum_a, prev, 16), lo_pn = __shfl_sync(FULL, cum_pn, prev, 16);
@@ -169,10 +178,9 @@ __device__ __forceinline__ int mix_nibble(Coder &k, uint64_t &st, const uint32_t
     } else { if (g.store0) const_cast<uint32_t *>(k.p)[k.left] = ((uint32_t)start & 0xffffu) | ((uint32_t)freq << 16); k.left++; }
     weights_update32(w, f_cm, f_nb, freq);
     const Grp gg = {FULL, g.shift, g.l16, writer, false, g.store0};
-    const int c2 = cdf_blend(gg, cc, mc, sym, cm_inc, cm_lim);
-    const int s2 = cdf_blend(gg, c, maxv, sym, nb_inc, nb_lim);
+    const int c2 = cdf_blend(gg, v.cc, v.mc, sym, cm_inc, cm_lim);
+    const int s2 = cdf_blend(gg, v.c, v.maxv, sym, nb_inc, nb_lim);
     if (writer) { *reinterpret_cast<int16_t *>(cm + 2 * g.l16) = (int16_t)c2; *reinterpret_cast<int16_t *>(nb + 2 * g.l16) = (int16_t)s2; }
-    return sym;
 }
 
 // Converged literal fast path: when both groups of the warp sit at the start of a literal byte, run whole bytes
@@ -360,24 +368,33 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
                 if (LPS == 16) m = min(m, __shfl_xor_sync(FULL, m, 16));
                 if (m == 0) break;
             }
+            // search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo); the stride tables
+            // of the two nibbles are distinct and so are their context-map regions (FirstNibble / SecondNibble), so an
+            // early load never overtakes a store to the same CDF
+            char *nbh = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * 32u, *cmh = cmb + ctx * 32u;
+            __syncwarp();
+            MixVals vh = mix_load(g, nbh, cmh);
             for (uint32_t i = 0; i < m; i++) {
                 const uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
                 const uint32_t byte_in = ENC ? src[done + i] : 0u;
+                const MixSym sh_ = mix_search<ENC>(k.a, g, vh, wh, (int)(byte_in >> 4));
+                const uint32_t h = (uint32_t)sh_.sym;
+                const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = (h & fc) | ((ctx & o1) << 4);
+                char *const nbl = lo_tab + (ic * 256u + ib) * 32u, *const cml = cmb + (256u + h + 16u * ctx) * 32u;
                 __syncwarp();
-                const int h = mix_nibble<ENC>(k, k.a, wbase, wi, wmax, g, writer, hi_tab + (ctx * 256u + (ssb & mm & (~o1 & 0xffu))) * 32u, cmb + ctx * 32u,
-                                              wh, inc, lim, ch_inc, ch_lim, (int)(byte_in >> 4));
-                const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = ((uint32_t)h & fc) | ((ctx & o1) << 4);
-                __syncwarp();
-                const int l = mix_nibble<ENC>(k, k.b, wbase, wi, wmax, g, writer, lo_tab + (ic * 256u + ib) * 32u, cmb + (256u + (uint32_t)h + 16u * ctx) * 32u,
-                                              wl, inc, lim, cl_inc, cl_lim, (int)(byte_in & 0xf));
-                const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
+                const MixVals vl = mix_load(g, nbl, cml);
+                mix_finish<ENC>(k, k.a, wbase, wi, wmax, g, writer, nbh, cmh, vh, sh_, wh, inc, lim, ch_inc, ch_lim);
+                const MixSym sl_ = mix_search<ENC>(k.b, g, vl, wl, (int)(byte_in & 0xf));
+                const uint32_t cur = ((uint32_t)sl_.sym | (h << 4)) & 0xff;
                 l8 = (l8 >> 8) | ((unsigned long long)cur << 56);
                 if (g.store0) dst[done + i] = (uint8_t)cur;
-                uint32_t sel;
-                if (pm == 0) sel = cur & 0x3f;
-                else if (pm == 1) sel = cur >> 2;
-                else sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
+                uint32_t sel = (cur >> (pm == 1 ? 2u : 0u)) & 0x3fu;
+                if (pm >= 2) sel = __ldg(lut + cur) | __ldg(lut + 256 + ((uint32_t)(l8 >> 48) & 0xff));
                 ctx = lcm[sel];
+                nbh = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * 32u; cmh = cmb + ctx * 32u;
+                __syncwarp();
+                vh = mix_load(g, nbh, cmh);   // speculative on the last byte: initialised slabs
+                mix_finish<ENC>(k, k.b, wbase, wi, wmax, g, writer, nbl, cml, vl, sl_, wl, inc, lim, cl_inc, cl_lim);
             }
             done += m;
             if (!ENC) k.sym_count += 2 * m;
