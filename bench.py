@@ -136,7 +136,11 @@ def run_reference_arm(args):
     v = args.steps * blob.size / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
-            "data": "synthetic", "config": {"workload": "%d x 64 KiB synthetic-text divANS streams (bounded sample of configs[1])" % n_sample},
+            "data": "synthetic",
+            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[1]), literal-only "
+                                   "encoding (1 PredictionMode + 1 Literal command)" % args.streams,
+                       "streams_per_gpu": args.streams, "stream_bytes": STREAM_BYTES,
+                       "sample": "each step decodes a bounded sample of %d of these streams on the host CPU" % n_sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d streams per step, all %d host threads" % (n_sample, threads)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
