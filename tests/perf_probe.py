@@ -25,10 +25,10 @@ run("text 64KiB default", raws, divans_b200.encode_options(), eng)
 run("text 64KiB dcm=1", raws, divans_b200.encode_options(dynamic_context_mixing=1), eng)
 run("text 64KiB dcm=2", raws, divans_b200.encode_options(dynamic_context_mixing=2), eng)
 run("text 64KiB utf8 mix=1 ", raws, divans_b200.encode_options(literal_pred_mode=2, literal_mixing_value=1), eng)
-if "--lz" in sys.argv:
+if "--lz" in sys.argv or "--lz-all" in sys.argv:
     sys.path.insert(0, "/root/repo")
     from oracle import oracle_py as O
-    m = min(n, 512)
+    m = n if "--lz-all" in sys.argv else min(n, 512)
     cl = [O.Commands.lz77(r, 16, 2, 4).serialize() for r in raws[:m]]
     run("text 64KiB lz77 cmds (w16)", raws[:m], divans_b200.encode_options(window_size=16), eng, cmds=cl)
 for p in (0.5, 0.9, 0.99):
