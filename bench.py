@@ -42,23 +42,56 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML in-process every
+    ~10 ms when nvidia_ml_py is importable, else the `nvidia-smi --query-gpu` line the recipe gives (one call ~0.1 s)."""
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.uuid, self.samples, self._halt = index, uuid, [], threading.Event()
+        self.source = "nvidia-smi"
         self.q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                   "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if isinstance(uuid, bytes) else str(uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._nv, self._h, self.source = pynvml, h, "nvml"
+        except Exception:
+            self._nv = None
+
+    def _nvml_sample(self):
+        nv = self._nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        act = lambda m: "Active" if bits & m else "Not Active"   # nvml.h: SwPowerCap 0x4, HwSlowdown 0x8, SwThermal 0x20, HwThermal 0x40
+        return [str(mhz), str(self._max), "", act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         while not self._halt.is_set():
             try:
+                if self._nv is not None:
+                    self.samples.append(self._nvml_sample())
+                    self._halt.wait(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
-                pass
+                self._nv = None if self._nv is not None and not self.samples else self._nv
             self._halt.wait(0.1)
 
     def stop(self):
@@ -73,7 +106,8 @@ class ClockSampler(threading.Thread):
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def make_inputs(rank, n_streams, engine=None):
@@ -211,7 +245,11 @@ def main():
     assert bool((d_status == 0).all()) and bool((d_out_len == STREAM_BYTES).all()), "decode failed"
     assert bool((d_out[:out_bytes].cpu().numpy() == blob).all()), "GPU output differs from the original input"
     launches0 = eng.launch_count
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     main_ms = []
