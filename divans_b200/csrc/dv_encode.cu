@@ -15,7 +15,7 @@
 namespace dv {
 
 template <int LPS>
-__global__ void __launch_bounds__(DECODE_BLOCK_THREADS) encode_model_kernel(EncodeParams p) {
+__global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(EncodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;

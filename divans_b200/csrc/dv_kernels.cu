@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) demux_kernel(FrameParams p, uint8_t *payl
 // LPS == 32 keeps the north-star "one warp owns one stream" layout: the upper half-warp mirrors the lower one.
 // ---------------------------------------------------------------------------------------------------------------
 template <int LPS>
-__global__ void __launch_bounds__(DECODE_BLOCK_THREADS) decode_kernel(DecodeParams p) {
+__global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
