@@ -37,6 +37,7 @@ BATCH_SYMBOLS = [
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
     "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device", "divans_b200_ir_to_cmds",
+    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait",
 ]
 
 
@@ -87,6 +88,10 @@ def load_library():
     batch = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     L.divans_b200_decode_batch_host.argtypes = batch + [ctypes.c_uint32]
     L.divans_b200_decode_batch_host.restype = ctypes.c_uint8
+    L.divans_b200_decode_batch_host_async.argtypes = batch + [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32)]
+    L.divans_b200_decode_batch_host_async.restype = ctypes.c_uint8
+    L.divans_b200_decode_batch_host_wait.argtypes = [vp, ctypes.c_int32]
+    L.divans_b200_decode_batch_host_wait.restype = ctypes.c_uint8
     L.divans_b200_decode_batch_device.argtypes = batch + [ctypes.c_uint64, ctypes.c_uint32, vp]
     L.divans_b200_decode_batch_device.restype = ctypes.c_uint8
     L.divans_b200_encode_options_default.argtypes = [ctypes.POINTER(EncodeOptions)]
@@ -208,6 +213,30 @@ class Engine:
         if rc != DIVANS_SUCCESS:
             raise DivansError("decode_batch_host: " + self._err())
         return out_len, status
+
+    def decode_batch_host_async(self, in_blob, in_off, in_len, out, out_off, out_cap, flags=0):
+        """Pipelined host-buffer decode: returns a pending-batch handle; ``handle.wait()`` -> (out_len, status).  At most two
+        batches in flight; pass pinned ``in_blob`` / ``out`` (e.g. torch pinned tensors' numpy views) for the copies to
+        overlap the kernels of the neighbouring batches."""
+        n = len(in_off)
+        keep = [np.ascontiguousarray(in_off, np.uint64), np.ascontiguousarray(in_len, np.uint64),
+                np.ascontiguousarray(out_off, np.uint64), np.ascontiguousarray(out_cap, np.uint64)]
+        out_len = np.zeros(n, np.uint64)
+        status = np.full(n, DIVANS_FAILURE, np.int32)
+        ticket = ctypes.c_int32(-1)
+        rc = self._L.divans_b200_decode_batch_host_async(self._h, n, _ptr(in_blob), _ptr(keep[0]), _ptr(keep[1]), _ptr(out), _ptr(keep[2]),
+                                                         _ptr(keep[3]), _ptr(out_len), _ptr(status), flags, ctypes.byref(ticket))
+        if rc != DIVANS_SUCCESS:
+            raise DivansError("decode_batch_host_async: " + self._err())
+        eng = self
+
+        class _Pending:
+            def wait(self_inner):
+                if eng._L.divans_b200_decode_batch_host_wait(eng._h, ticket.value) != DIVANS_SUCCESS:
+                    raise DivansError("decode_batch_host_wait: " + eng._err())
+                _ = keep, in_blob, out      # the buffers stay referenced until the batch is complete
+                return out_len, status
+        return _Pending()
 
     def decode_batch_device(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, n, in_total_bytes, flags=0, stream=None):
         """All arguments are raw device pointers (ints), e.g. ``tensor.data_ptr()``.  Asynchronous."""

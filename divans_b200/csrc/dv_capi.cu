@@ -44,6 +44,18 @@ struct divans_b200_ctx {
     uint8_t *d_in = nullptr; size_t d_in_cap = 0;
     uint8_t *d_out = nullptr; size_t d_out_cap = 0;
     uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;   // in_off,in_len,out_off,out_cap,out_len (+status)
+    // pipelined host API (decode_batch_host_async): two batches in flight, copies on their own streams
+    struct Lane {
+        uint8_t *d_in = nullptr; size_t d_in_cap = 0;
+        uint8_t *d_out = nullptr; size_t d_out_cap = 0;
+        uint64_t *d_meta = nullptr; size_t d_meta_cap = 0;
+        cudaEvent_t e_in = nullptr, e_k = nullptr, e_out = nullptr;
+        uint8_t *h_res = nullptr; size_t h_res_cap = 0;      // pinned staging of out_len[] + status[] (the caller's arrays may be pageable)
+        uint64_t *u_out_len = nullptr; int32_t *u_status = nullptr; size_t n = 0;
+        bool pending = false;
+    } lane[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    uint64_t async_seq = 0;
     uint32_t *d_sf = nullptr; size_t sf_cap = 0;               // encoder: symbol logs
     uint8_t *d_replay = nullptr; size_t replay_cap = 0;
     uint32_t *d_enc_scratch = nullptr; size_t enc_scratch_cap = 0;
@@ -125,6 +137,15 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     if (ctx->evm) cudaEventDestroy(ctx->evm);
     if (ctx->evm1) cudaEventDestroy(ctx->evm1);
     cudaFree(ctx->d_sf); cudaFree(ctx->d_replay); cudaFree(ctx->d_enc_scratch); cudaFree(ctx->d_pm_internal); cudaFree(ctx->d_rcp15);
+    for (auto &ln : ctx->lane) {
+        cudaFree(ln.d_in); cudaFree(ln.d_out); cudaFree(ln.d_meta);
+        if (ln.h_res) cudaFreeHost(ln.h_res);
+        if (ln.e_in) cudaEventDestroy(ln.e_in);
+        if (ln.e_k) cudaEventDestroy(ln.e_k);
+        if (ln.e_out) cudaEventDestroy(ln.e_out);
+    }
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -242,6 +263,79 @@ extern "C" void divans_b200_encode_options_default(divans_b200_encode_options *o
     o->window_size = 22; o->dynamic_context_mixing = 0; o->prior_depth = 0; o->use_context_map = 1; o->force_stride = 9;
     o->literal_pred_mode = 0; o->literal_mixing_value = 4;
 }
+// ---- pipelined host-buffer decode: H2D of batch k+1 and D2H of batch k-1 overlap the kernels of batch k ----
+extern "C" DivansResult divans_b200_decode_batch_host_wait(divans_b200_ctx *ctx, int32_t ticket) {
+    if (!ctx || ticket < 0 || ticket > 1) return DIVANS_FAILURE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    divans_b200_ctx::Lane &ln = ctx->lane[ticket];
+    if (!ln.pending) return DIVANS_SUCCESS;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ln.e_out));
+    memcpy(ln.u_out_len, ln.h_res, ln.n * 8);
+    memcpy(ln.u_status, ln.h_res + ln.n * 8, ln.n * 4);
+    ln.pending = false;
+    return DIVANS_SUCCESS;
+}
+extern "C" DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                                            const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                                            const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags,
+                                                            int32_t *ticket) {
+    if (!ctx || !ticket) return DIVANS_FAILURE;
+    if (n == 0) { *ticket = 0; return DIVANS_SUCCESS; }
+    int t;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        t = (int)(ctx->async_seq++ & 1);
+    }
+    if (ctx->lane[t].pending && divans_b200_decode_batch_host_wait(ctx, t) != DIVANS_SUCCESS) return DIVANS_FAILURE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    divans_b200_ctx::Lane &ln = ctx->lane[t];
+    if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
+    if (!ln.e_in) {
+        CK(cudaEventCreateWithFlags(&ln.e_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ln.e_k, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.e_out, cudaEventDisableTiming));
+    }
+    uint64_t in_end = 0, out_lo = ~0ull, out_hi = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
+        if (out_off[i] < out_lo) out_lo = out_off[i];
+        if (out_off[i] + out_cap[i] > out_hi) out_hi = out_off[i] + out_cap[i];
+    }
+    // (re)allocation of a lane's buffers synchronises the device: only while the pipeline warms up
+    if (!grow(ctx, &ln.d_in, &ln.d_in_cap, (size_t)in_end + 64)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ln.d_out, &ln.d_out_cap, (size_t)out_hi + 64)) return DIVANS_FAILURE;
+    if (!grow(ctx, &ln.d_meta, &ln.d_meta_cap, n * 6)) return DIVANS_FAILURE;
+    if (ln.h_res_cap < n * 12) {
+        if (ln.h_res) cudaFreeHost(ln.h_res);
+        ln.h_res = nullptr; ln.h_res_cap = 0;
+        CK(cudaMallocHost((void **)&ln.h_res, n * 12 + 64));
+        ln.h_res_cap = n * 12 + 64;
+    }
+    ln.u_out_len = out_len; ln.u_status = status; ln.n = n;
+    uint64_t *m = ln.d_meta;
+    CK(cudaMemcpyAsync(ln.d_in, in, in_end, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(m, in_off, n * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(m + n, in_len, n * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(m + 2 * n, out_off, n * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(m + 3 * n, out_cap, n * 8, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ln.e_in, ctx->s_h2d));
+    CK(cudaStreamWaitEvent(ctx->stream, ln.e_in, 0));
+    int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
+    DivansResult r = divans_b200_decode_batch_device(ctx, n, ln.d_in, m, m + n, ln.d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status, in_end,
+                                                     flags, ctx->stream);
+    if (r != DIVANS_SUCCESS) return r;
+    CK(cudaEventRecord(ln.e_k, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ln.e_k, 0));
+    CK(cudaMemcpyAsync(ln.h_res, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaMemcpyAsync(ln.h_res + n * 8, d_status, n * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (out_hi > out_lo) CK(cudaMemcpyAsync(out + out_lo, ln.d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(ln.e_out, ctx->s_d2h));
+    ln.pending = true;
+    *ticket = t;
+    return DIVANS_SUCCESS;
+}
+
 // ---- encoder ----
 static inline int pack_speed(const int16_t sp[2]) { return (int)((uint32_t)(uint16_t)sp[0] | ((uint32_t)(uint16_t)sp[1] << 16)); }
 

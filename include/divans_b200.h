@@ -122,6 +122,17 @@ float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx);
 DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
                                            const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                            const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags);
+/* Pipelined variant of divans_b200_decode_batch_host for back-to-back batches: the call enqueues the H2D copies, the
+ * kernels and the D2H copies on the context's copy / compute streams and returns a ticket (0 or 1; at most two batches
+ * in flight, a third call first waits for the oldest).  The copies of one batch overlap the kernels of its neighbours.
+ * `in` / `out` must stay valid (and should be pinned, else the copies degrade to synchronous ones) until
+ * divans_b200_decode_batch_host_wait(ctx, ticket) returns; out_len[] / status[] are filled by the wait call; the whole
+ * [min out_off, max out_off + out_cap) range of `out` is written. */
+DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
+                                                 const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                                 const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags,
+                                                 int32_t *ticket);
+DivansResult divans_b200_decode_batch_host_wait(divans_b200_ctx *ctx, int32_t ticket);
 /* Same, all pointers are DEVICE pointers (inputs already resident in HBM, outputs left in HBM).
  * `in_total_bytes` = size of the d_in blob (upper bound of sum(in_len)); `cuda_stream` is a cudaStream_t (NULL = the
  * context's own stream).  Asynchronous: returns after enqueueing. */

@@ -224,3 +224,37 @@ def test_corrupted_streams_without_crc_never_hang(engine, oracle, text):
         assert all(st in (0, 1, 2, 3) for st, _ in res)
     (st, out), = engine.decode([base[-1]], [1 << 20])
     assert st == 0 and out == text[5 * 9000: 5 * 9000 + 20000]
+
+
+def test_pipelined_host_api_matches_blocking_call(engine, oracle, text):
+    # divans_b200_decode_batch_host_async / _wait: several batches back to back, two in flight, different contents per batch
+    import torch
+    batches = []
+    for b in range(5):
+        raws = [text[(b * 37 + i) * 1000: (b * 37 + i) * 1000 + 3000 + 997 * i] for i in range(24)]
+        streams = [oracle.encode_raw(r, oracle.options(window_size=12 + (i % 6))) for i, r in enumerate(raws)]
+        in_len = np.array([len(s) for s in streams], np.uint64)
+        in_off = np.zeros(len(streams), np.uint64)
+        in_off[1:] = np.cumsum((in_len + np.uint64(15)) & ~np.uint64(15))[:-1]
+        blob = torch.zeros(int(in_off[-1] + in_len[-1]) + 16, dtype=torch.uint8).pin_memory()
+        for s, o in zip(streams, in_off):
+            blob.numpy()[int(o):int(o) + len(s)] = np.frombuffer(s, np.uint8)
+        cap = np.array([len(r) for r in raws], np.uint64)
+        out_off = np.zeros(len(raws), np.uint64)
+        out_off[1:] = np.cumsum((cap + np.uint64(63)) & ~np.uint64(63))[:-1]
+        out = torch.zeros(int(out_off[-1] + cap[-1]) + 64, dtype=torch.uint8).pin_memory()
+        batches.append((raws, blob, in_off, in_len, out, out_off, cap))
+    pend = []
+    for raws, blob, in_off, in_len, out, out_off, cap in batches:
+        pend.append(engine.decode_batch_host_async(blob.numpy(), in_off, in_len, out.numpy(), out_off, cap))
+        if len(pend) == 2:
+            pend.pop(0).wait()
+    results = [p.wait() for p in pend]
+    assert len(results) >= 1
+    for raws, blob, in_off, in_len, out, out_off, cap in batches:
+        o = out.numpy()
+        for r, oo in zip(raws, out_off):
+            assert o[int(oo):int(oo) + len(r)].tobytes() == r
+    # and the out_len / status arrays of the last batch
+    ol, st = results[-1]
+    assert (st == 0).all() and (ol == batches[-1][6]).all()
