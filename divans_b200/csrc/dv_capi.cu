@@ -200,6 +200,7 @@ extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, si
     dp.in = d_in; dp.in_off = d_in_off; dp.in_len = d_in_len; dp.out = d_out; dp.out_off = d_out_off; dp.out_cap = d_out_cap;
     dp.out_len = d_out_len; dp.status = d_status; dp.frame = ctx->d_frame; dp.payload = ctx->d_payload; dp.n_streams = (uint32_t)n;
     dp.work_counter = ctx->d_counter; dp.arena = ctx->d_arena; dp.tables = ctx->d_tables; dp.nibble_counts = ctx->d_nibbles;
+    dp.model_rev = (flags & DIVANS_B200_FLAG_MODEL_WASM_2018) ? 1u : 0u;
     static const bool dbg = getenv("DIVANS_B200_DEBUG") != nullptr;
     static const bool skip_decode = getenv("DIVANS_B200_SKIP_DECODE") != nullptr;
     CK(cudaEventRecord(ctx->ev0, st));
@@ -393,6 +394,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     ep.window_size = window; ep.dynamic_context_mixing = o->dynamic_context_mixing & 0xff; ep.prior_depth = o->prior_depth & 0xff;
     ep.use_context_map = o->use_context_map; ep.force_stride = o->force_stride; ep.have_literal_adaptation = o->have_literal_adaptation;
     for (int k = 0; k < 4; k++) ep.literal_adaptation[k] = pack_speed(o->literal_adaptation[k]);
+    ep.model_rev = o->model_rev == DIVANS_B200_MODEL_WASM_2018 ? 1 : 0;
     CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
     CK(cudaEventRecord(ctx->ev0, st));
     CK(cudaEventRecord(ctx->evm, st));

@@ -86,6 +86,7 @@ struct DecodeParams {
     uint8_t *arena;             // n_slots * SLOT_STRIDE
     const uint8_t *tables;      // brotli tables blob
     uint64_t *nibble_counts;    // optional [2] totals (cmd, lit) for profiling
+    uint32_t model_rev;         // 0 = the reference tree as mounted; 1 = DIVANS_B200_MODEL_WASM_2018 (include/divans_b200.h)
 };
 
 struct FrameParams {
@@ -123,6 +124,7 @@ struct EncodeParams {
     // options (reference: DivansCompressorOptions, src/interface.rs:444-484)
     int window_size, dynamic_context_mixing, prior_depth, use_context_map, force_stride, have_literal_adaptation;
     int literal_adaptation[4];    // packed inc | lim << 16
+    int model_rev;                // see DecodeParams::model_rev
 };
 constexpr uint32_t PM_RECORD_BYTES = 32 + 16384 + 1024 + 8192;
 

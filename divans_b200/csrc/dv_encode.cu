@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
     s.tables = p.tables;
     s.state = S_IDLE;
     s.c->in.cmds = nullptr; s.c->in.n_cmds = 0; s.c->in.pos = 0; s.c->in.n_pms = 0; s.c->in.pms = nullptr; s.c->in.lits = nullptr;
+    s.c->model_rev = (uint32_t)p.model_rev;
     s.c->sidx = 0; s.c->raw_len = 0; s.c->lit_log_cap = p.lit_cap;
     s.out = p.replay + (uint64_t)slot * p.replay_stride; s.out_pos = 0;
     s.c->out_cap = p.replay_stride > 0xffffffffull ? 0xffffffffu : (uint32_t)p.replay_stride;

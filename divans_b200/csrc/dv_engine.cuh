@@ -91,6 +91,7 @@ struct Cold {
     uint32_t out_cap, ring_len, raw_len;
     uint32_t lit_log_cap;                    // encoder: capacity (entries) of the literal coder's log
     uint32_t sidx;                           // stream index being processed
+    uint32_t model_rev;                      // DecodeParams::model_rev
     // encoder
     CmdIn in;
     uint32_t e0, e1, e2, e3;                 // current input command fields

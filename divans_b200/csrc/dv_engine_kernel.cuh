@@ -240,11 +240,14 @@ template <bool ENC> __device__ __forceinline__ void enter_pm_map_mnemonic(St &s,
             if (target == ((cmap_max(s) + 1) & 0xff)) sym = 13;
         }
     }
-    set_next<ENC>(nx, A_misc(s, MI_PRED + PM_MNEMONIC + (int)s.f2), SPK_MED, sym);
+    // context_map.rs:273 + codec/priors.rs:130: Mnemonic has its own slots.  The build that produced the reference-held
+    // stream wasm/wasm.html:98-107 coded both mnemonics with the slot DynamicContextMixingSpeed / PriorDepth /
+    // ContextMapSpeedPalette[0] share (model_rev 1, include/divans_b200.h).
+    set_next<ENC>(nx, A_misc(s, MI_PRED + (s.c->model_rev ? PM_SPEED_PALETTE : PM_MNEMONIC + (int)s.f2)), SPK_MED, sym);
 }
 template <bool ENC> __device__ __forceinline__ void enter_pm_mixval(St &s, Next &nx) {
     s.state = S_PM_MIXVAL;
-    uint32_t prior = s.f1 >= 256 ? (uint32_t)(A_mix(s)[s.f1 - 256] & 0xf) : 16u;
+    uint32_t prior = (s.f1 >= 256 && !s.c->model_rev) ? (uint32_t)(A_mix(s)[s.f1 - 256] & 0xf) : 16u;   // context_map.rs:395-399; model_rev 1: always slot 16
     int sym = 0;
     if (ENC) sym = !s.c->desired_do_context_map ? 4 : (!(s.f3 & 1) ? 0 : (int)pm_rec<ENC>(s)[32 + 16384 + 1024 + s.f1]);
     set_next<ENC>(nx, A_misc(s, MI_PRED + PM_MIXING_VALUE + (int)prior), SPK_PLANE, sym);
@@ -362,7 +365,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
                 s.state = S_CP_DIST_BEG;
                 uint32_t dlen = bitlen32(s.c->e0);
                 int sym = (int)min(14u, (dlen - 1u) & 0xffu);
-                if (ENC && (s.c->lru1 - 3u) == s.c->e0) sym = 15;
+                if (ENC && (s.c->lru1 - 3u) == s.c->e0 && !s.c->model_rev) sym = 15;   // copy.rs:199-201 (the model_rev 1 encoder did not take the shortcut)
                 set_next<ENC>(nx, dprior_slab(s, g, s.f3) + (DP_DIST_BEG + (bitlen32(s.f0) >> 2)) * 16, SPK_SLOW, sym);
             }
         } else if (s.state == S_CP_DIST_BEG) {

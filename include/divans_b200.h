@@ -100,6 +100,16 @@ typedef struct divans_b200_ctx divans_b200_ctx;
 
 #define DIVANS_B200_FLAG_SKIP_CRC 1u      /* same meaning as the reference's skip_crc (ffi/mod.rs:213) */
 #define DIVANS_B200_FLAG_NO_CRC_KERNEL 2u /* do not even run the CRC kernel (trailer magic still checked) */
+/* Model revision.  Default (0) = the reference tree as mounted.  DIVANS_B200_MODEL_WASM_2018 = the build that produced the
+ * one compressed stream the reference tree holds (wasm/wasm.html:98-107): inside the PredictionMode command it codes the
+ * context-map mnemonic nibbles (codec/context_map.rs:273) with the prior that DynamicContextMixingSpeed / PriorDepth /
+ * ContextMapSpeedPalette[0] share (today: PredictionModePriorType::Mnemonic's own slots, codec/priors.rs:130) and every
+ * mixing value (:395-405) with prior slot 16 (today: value[i - 256] & 15 for i >= 256); its encoder also never used
+ * the `distance_lru[1] - 3` distance shortcut (codec/copy.rs:199-201).  Everything else is identical.  With the flag the
+ * GPU decodes that stream bit-exactly and the GPU encoder reproduces its 113 bytes (tests/test_gpu_parity.py). */
+#define DIVANS_B200_MODEL_CURRENT 0
+#define DIVANS_B200_MODEL_WASM_2018 1
+#define DIVANS_B200_FLAG_MODEL_WASM_2018 4u
 
 /* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
 
@@ -154,6 +164,7 @@ typedef struct {
     int16_t literal_adaptation[4][2];
     int32_t literal_pred_mode;      /* internal literal-only compressor: LSB6=0 MSB6=1 UTF8=2 SIGN=3 */
     int32_t literal_mixing_value;   /* internal literal-only compressor: value of all 8192 mixing entries (reference: 4) */
+    int32_t model_rev;              /* DIVANS_B200_MODEL_CURRENT (default) or DIVANS_B200_MODEL_WASM_2018 */
 } divans_b200_encode_options;
 void divans_b200_encode_options_default(divans_b200_encode_options *o);
 

@@ -510,11 +510,14 @@ typedef struct {
     dvo_cdf16 *lit_high_priors, *lit_low_priors;
     /* the single recycled PredictionMode scratch (codec/context_map.rs:69-94, threading.rs:494-526) */
     uint8_t pm_lit_map[16384]; uint8_t pm_dist_map[1024]; uint8_t pm_mixing[8192];
+    uint32_t pm_map_len[2]; uint8_t pm_f8[4][2], pm_mode; /* what the last PredictionMode command carried (for dvo_decode_cmds) */
     /* coders + ring */
     coder cmd, lit;
     recoder rc;
     int mixing_trait; /* specializations.rs:26-36 */
     uint64_t n_cmds;
+    int model_rev;    /* DVO_MODEL_CURRENT / DVO_MODEL_WASM_2018: see divans_oracle.h */
+    dvo_cmdlist *rec; /* decoder: when non-NULL every decoded command is appended here */
 } codec;
 
 static void set_pred_mode_luts(codec *s, uint8_t mode) {
@@ -758,7 +761,8 @@ static int code_copy(codec *s, uint32_t *dist_io, uint32_t *num_io) {
             if (!ok) return DVO_FAILURE; /* CopyDistanceMnemonicCodeBad */
         } else {
             uint8_t bn = (uint8_t)(dlen - 1); if (bn > 14) bn = 14;
-            if ((uint32_t)(s->distance_lru[1] - 3u) == in_dist) bn = 15;
+            /* copy.rs:199-201; the DVO_MODEL_WASM_2018 encoder did not take this shortcut (the decoder accepts both) */
+            if ((uint32_t)(s->distance_lru[1] - 3u) == in_dist && !(s->cmd.encoding && s->model_rev == DVO_MODEL_WASM_2018)) bn = 15;
             uint32_t index = bitlen32(num_bytes) >> 2;
             bn = code_and_blend(&s->cmd, bn, P(s->copy_priors, T_CP, CP_DistanceBegNib, ap, index, 0), SPEED_SLOW);
             if (bn == 15) {
@@ -876,8 +880,13 @@ static int code_context_map(codec *s, int is_distance, const uint8_t *in_map, ui
             for (int i = 0; i < 13; i++) { if (s->cmap_lru[i] == target) mn = (uint8_t)i; if (s->cmap_lru[i] > mx) mx = s->cmap_lru[i]; }
             if (target == (uint8_t)(mx + 1)) mn = 13;
         }
-        mn = code_and_blend(&s->cmd, mn, P(s->pred_priors, T_PM, PM_Mnemonic, is_distance, 0, 0), sp);
-        if (mn == 14) return DVO_SUCCESS;
+        /* context_map.rs:273 + codec/priors.rs:130: Mnemonic has its own four slots.  DVO_MODEL_WASM_2018 (the build
+         * that produced wasm/wasm.html:98-107): both mnemonic priors are the CDF that ContextMapSpeedPalette[0],
+         * DynamicContextMixingSpeed and PriorDepth share (the priors.rs:226-236 fall-through slot). */
+        dvo_cdf16 *mn_prior = s->model_rev == DVO_MODEL_WASM_2018 ? P(s->pred_priors, T_PM, PM_ContextMapSpeedPalette, 0, 0, 0)
+                                                                  : P(s->pred_priors, T_PM, PM_Mnemonic, is_distance, 0, 0);
+        mn = code_and_blend(&s->cmd, mn, mn_prior, sp);
+        if (mn == 14) { s->pm_map_len[is_distance] = index; return DVO_SUCCESS; }
         uint8_t val;
         if (mn == 15) {
             uint8_t msn = index >= in_len ? 0 : (uint8_t)(in_map[index] >> 4);
@@ -956,7 +965,8 @@ static int code_predmode(codec *s, const dvo_predmode *in) {
         else if (!s->desired_do_context_map) mv = 4;
         else if (!combine) mv = 0;
         else mv = in ? in->mixing[index] : 0;
-        uint32_t prior = index >= 256 ? (uint32_t)(s->pm_mixing[index - 256] & 0xf) : 16u;
+        /* context_map.rs:395-399; DVO_MODEL_WASM_2018: one prior (slot 16) for every mixing value */
+        uint32_t prior = (index >= 256 && s->model_rev != DVO_MODEL_WASM_2018) ? (uint32_t)(s->pm_mixing[index - 256] & 0xf) : 16u;
         mv = code_and_blend(&s->cmd, mv, P(s->pred_priors, T_PM, PM_PriorMixingValue, prior, 0, 0), SPEED_PLANE);
         s->pm_mixing[index] = mv;
     }
@@ -971,6 +981,7 @@ static int code_predmode(codec *s, const dvo_predmode *in) {
         s->literal_adaptation[k].inc = dvo_u8_to_speed(a);
         s->literal_adaptation[k].lim = dvo_u8_to_speed(b);
     }
+    memcpy(s->pm_f8, f8, sizeof f8); s->pm_mode = pm;
     memcpy(s->literal_context_map, s->pm_lit_map, 16384);
     memcpy(s->mixing_mask, s->pm_mixing, 8192);
     s->mixing_trait = (s->model_weights[0].mixing_param > 1) || (s->model_weights[1].mixing_param > 1);
@@ -1051,8 +1062,23 @@ size_t dvo_mux_single(int stream_id, const uint8_t *data, size_t n, uint8_t *out
 /* ------------------------------------------------------------------------------------------
  * whole-stream decode  (divans_decompressor.rs:38-52,111-161 ; codec/decoder.rs:230-419 ; codec/mod.rs:652-1024)
  * ------------------------------------------------------------------------------------------ */
-int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc,
-                  size_t *in_consumed, uint64_t *n_cmd_nibbles, uint64_t *n_lit_nibbles) {
+static dvo_cmd *cl_add(dvo_cmdlist *l);
+static size_t cl_add_lit(dvo_cmdlist *l, const uint8_t *p, size_t n);
+static dvo_predmode *cl_add_pm(dvo_cmdlist *l);
+static void record_predmode(codec *s) {
+    dvo_cmd *c = cl_add(s->rec); c->type = DVO_CMD_PREDMODE; c->a = (uint32_t)s->rec->n_pms;
+    dvo_predmode *pm = cl_add_pm(s->rec);
+    pm->pred_mode = s->pm_mode; pm->has_speeds = 1;
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) {
+        pm->stride_speed[k][j] = pm->combined_speed[k][j] = brotli_u8_to_speed(s->pm_f8[k][j]);
+        pm->cm_speed[k][j] = brotli_u8_to_speed(s->pm_f8[2 + k][j]);
+    }
+    pm->lit_map_len = s->pm_map_len[0]; memcpy(pm->lit_map, s->pm_lit_map, pm->lit_map_len);
+    pm->dist_map_len = s->pm_map_len[1]; memcpy(pm->dist_map, s->pm_dist_map, pm->dist_map_len);
+    memcpy(pm->mixing, s->pm_mixing, 8192);
+}
+static int decode_impl(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc,
+                       size_t *in_consumed, uint64_t *n_cmd_nibbles, uint64_t *n_lit_nibbles, int model_rev, dvo_cmdlist *rec) {
     *out_len = 0;
     if (in_len < 16) return DVO_NEEDS_MORE_INPUT;
     if (in[0] != 0xff || in[1] != 0xe5 || in[2] != 0x8c || in[3] != 0x9f) return DVO_FAILURE;
@@ -1066,6 +1092,7 @@ int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap
     if (trailer + 8 > in_len) { free(cmdbuf); free(litbuf); return DVO_NEEDS_MORE_INPUT; }
     codec *s = (codec *)malloc(sizeof(codec));
     codec_init(s, window, 0);
+    s->model_rev = model_rev; s->rec = rec; if (rec) rec->window = window;
     ans_dec_init(&s->cmd.d, cmdbuf, cl); ans_dec_init(&s->lit.d, litbuf, ll);
     s->rc.out = out; s->rc.out_cap = out_cap;
     uint8_t *scratch = NULL; size_t scratch_cap = 0;
@@ -1080,11 +1107,13 @@ int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap
             uint32_t d = 0, nb = 0;
             rc = code_copy(s, &d, &nb); if (rc) break;
             obs_distance(s, d);
+            if (rec) { dvo_cmd *c = cl_add(rec); c->type = t; c->a = d; c->b = nb; }
             rc = rc_copy(&s->rc, d, nb); if (rc) break;
         } else if (t == DVO_CMD_DICT) {
             next_state(s); s->last_4_states |= 192;
             uint32_t id = 0, sz = 0, tr = 0, fs = 0;
             rc = code_dict(s, &id, &sz, &tr, &fs); if (rc) break;
+            if (rec) { dvo_cmd *c = cl_add(rec); c->type = t; c->a = id; c->b = sz; c->c = tr; c->d = fs; }
             rc = rc_dict(&s->rc, sz, id, tr, fs); if (rc) break;
         } else if (t == DVO_CMD_LITERAL) {
             next_state(s); s->last_4_states |= 128;
@@ -1096,18 +1125,23 @@ int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap
             memset(scratch, 0, len);
             code_literal_bytes(s, scratch, len);
             if (s->lit.d.underflow) { rc = DVO_NEEDS_MORE_INPUT; break; }
+            if (rec) { size_t off = cl_add_lit(rec, scratch, len); dvo_cmd *c = cl_add(rec); c->type = t; c->a = (uint32_t)off; c->b = len; c->c = (uint32_t)he; }
             for (uint32_t i = 0; i < len; i++) rc_put(&s->rc, scratch[i]);
         } else if (t == DVO_CMD_BTYPE_L) {
             uint8_t bt = code_btype(s, 0, 0);
             uint8_t stride = code_and_blend(&s->cmd, 0, P(s->btype_priors, T_BT, BT_StrideNibble, 0, 0, 0), SPEED_SLOW);
             obs_btype(s, 0, bt);
             s->btype_last = bt; s->stride = stride; /* obs_literal_block_switch, interface.rs:289-292 */
+            if (rec) { dvo_cmd *c = cl_add(rec); c->type = t; c->a = bt; c->b = stride; }
         } else if (t == DVO_CMD_BTYPE_C) {
             uint8_t bt = code_btype(s, 1, 0); obs_btype(s, 1, bt);
+            if (rec) { dvo_cmd *c = cl_add(rec); c->type = t; c->a = bt; }
         } else if (t == DVO_CMD_BTYPE_D) {
             uint8_t bt = code_btype(s, 2, 0); obs_btype(s, 2, bt);
+            if (rec) { dvo_cmd *c = cl_add(rec); c->type = t; c->a = bt; }
         } else if (t == DVO_CMD_PREDMODE) {
             rc = code_predmode(s, NULL); if (rc) break;
+            if (rec) record_predmode(s);
         } else { rc = DVO_FAILURE; break; } /* CommandCodeOutOfBounds */
         if (s->cmd.d.underflow || s->lit.d.underflow) { rc = DVO_NEEDS_MORE_INPUT; break; }
         if (s->rc.overflow) { rc = DVO_NEEDS_MORE_OUTPUT; break; }
@@ -1127,8 +1161,16 @@ int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap
     free(scratch); codec_free(s); free(s); free(cmdbuf); free(litbuf);
     return rc;
 }
+int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc,
+                  size_t *in_consumed, uint64_t *n_cmd_nibbles, uint64_t *n_lit_nibbles) {
+    return decode_impl(in, in_len, out, out_cap, out_len, skip_crc, in_consumed, n_cmd_nibbles, n_lit_nibbles, DVO_MODEL_CURRENT, NULL);
+}
 int dvo_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc) {
     return dvo_decode_ex(in, in_len, out, out_cap, out_len, skip_crc, NULL, NULL, NULL);
+}
+int dvo_decode_cmds(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc,
+                    int model_rev, dvo_cmdlist *cmds) {
+    return decode_impl(in, in_len, out, out_cap, out_len, skip_crc, NULL, NULL, NULL, model_rev, cmds);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1149,6 +1191,7 @@ int dvo_encode_cmds(const dvo_cmdlist *l, const dvo_options *o, uint8_t *out, si
     s->desired_context_mixing = (uint8_t)dcm; s->desired_prior_depth = (uint8_t)o->prior_depth;
     s->desired_do_context_map = o->use_context_map; s->desired_force_stride = o->force_stride;
     s->have_desired_adapt = o->have_literal_adaptation;
+    s->model_rev = o->model_rev;
     memcpy(s->desired_adapt, o->literal_adaptation, sizeof s->desired_adapt);
     int rc = DVO_SUCCESS;
     uint8_t *scratch = NULL; size_t scratch_cap = 0;

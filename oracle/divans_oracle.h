@@ -24,6 +24,20 @@
 extern "C" {
 #endif
 
+/* ---- model revisions ----
+ * DVO_MODEL_CURRENT   = the reference tree as mounted (dropbox/divans @ 23459c22).
+ * DVO_MODEL_WASM_2018 = the build that produced the one compressed stream the reference tree holds
+ *   (wasm/wasm.html:98-107, `_example_dv_file`, 113 bytes).  It differs from the current source in exactly two
+ *   constructs of the PredictionMode command, both in codec/context_map.rs:
+ *     (1) the context-map Mnemonic nibbles (:273) are coded with the prior that DynamicContextMixingSpeed, PriorDepth
+ *         and ContextMapSpeedPalette[0] share, not with PredictionModePriorType::Mnemonic's own slots
+ *         (codec/priors.rs:130);
+ *     (2) every mixing value (:395-405) is coded with prior slot 16, also for index >= 256 (today: value[i-256] & 15).
+ *   With these two the stream decodes to a CRC-valid plaintext; everything else (rANS, CDF arithmetic, command, literal,
+ *   copy, dictionary coding, framing, CRC32C) is the same code in both revisions.  See tests/test_oracle_kat.py. */
+#define DVO_MODEL_CURRENT 0
+#define DVO_MODEL_WASM_2018 1
+
 /* ---- result codes: reference src/ffi/interface.rs:8-12 ---- */
 #define DVO_SUCCESS 0
 #define DVO_NEEDS_MORE_INPUT 1
@@ -103,6 +117,7 @@ typedef struct {
     int force_stride;            /* 0..8, 9 = UseBrotliRec (default) */
     int have_literal_adaptation; /* Option<[Speed;4]> */
     dvo_speed literal_adaptation[4];
+    int model_rev;               /* DVO_MODEL_CURRENT (0, what dvo_options_default sets) or DVO_MODEL_WASM_2018 */
 } dvo_options;
 void dvo_options_default(dvo_options *o);
 
@@ -113,6 +128,10 @@ int dvo_decode(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, s
 /* like dvo_decode but also reports how many input bytes form the stream (header..trailer) */
 int dvo_decode_ex(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len,
                   int skip_crc, size_t *in_consumed, uint64_t *n_cmd_nibbles, uint64_t *n_lit_nibbles);
+/* decode with an explicit model revision; when `cmds` is non-NULL the decoded commands are appended to it (an
+ * initialised dvo_cmdlist), so that a stream can be re-encoded with dvo_encode_cmds */
+int dvo_decode_cmds(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *out_len, int skip_crc,
+                    int model_rev, dvo_cmdlist *cmds);
 /* encode a command list */
 int dvo_encode_cmds(const dvo_cmdlist *l, const dvo_options *o, uint8_t *out, size_t cap, size_t *out_len);
 /* the reference's internal literal-only compressor (raw_to_cmd/mod.rs:105-181): one PredictionMode

@@ -40,6 +40,7 @@ class Options(ctypes.Structure):
         ("force_stride", ctypes.c_int),
         ("have_literal_adaptation", ctypes.c_int),
         ("literal_adaptation", Speed * 4),
+        ("model_rev", ctypes.c_int),
     ]
 
 
@@ -68,6 +69,8 @@ def lib():
         L.dvo_decode.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, szp, ctypes.c_int]
         L.dvo_decode_ex.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, szp, ctypes.c_int, szp,
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+        L.dvo_decode_cmds.argtypes = [u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, szp, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(CmdList)]
         L.dvo_encode_raw.argtypes = [u8p, ctypes.c_size_t, ctypes.POINTER(Options), u8p, ctypes.c_size_t, szp]
         L.dvo_encode_cmds.argtypes = [ctypes.POINTER(CmdList), ctypes.POINTER(Options), u8p, ctypes.c_size_t, szp]
         L.dvo_parse_ir.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(CmdList)]
@@ -111,12 +114,16 @@ def _as_u8(b):
     return np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, np.uint8)
 
 
+MODEL_CURRENT, MODEL_WASM_2018 = 0, 1  # divans_oracle.h "model revisions"
+
+
 def options(window_size=22, dynamic_context_mixing=0, prior_depth=0, use_context_map=1, force_stride=9,
-            literal_adaptation=None):
+            literal_adaptation=None, model_rev=MODEL_CURRENT):
     o = Options()
     lib().dvo_options_default(ctypes.byref(o))
     o.window_size, o.dynamic_context_mixing, o.prior_depth = window_size, dynamic_context_mixing, prior_depth
     o.use_context_map, o.force_stride = use_context_map, force_stride
+    o.model_rev = model_rev
     if literal_adaptation is not None:
         o.have_literal_adaptation = 1
         for i, (a, b) in enumerate(literal_adaptation):
@@ -143,6 +150,19 @@ def decode(data, out_cap=None, skip_crc=False, stats=False):
     if stats:
         return rc, res, dict(consumed=consumed.value, cmd_nibbles=nc.value, lit_nibbles=nl.value)
     return rc, res
+
+
+def decode_cmds(data, out_cap=None, skip_crc=False, model_rev=MODEL_CURRENT):
+    """decode with an explicit model revision; returns (rc, bytes, Commands holding the decoded command list)."""
+    d = _as_u8(data)
+    if out_cap is None:
+        out_cap = max(1 << 16, d.size * 64)
+    out = np.empty(out_cap, np.uint8)
+    n = ctypes.c_size_t(0)
+    cl = Commands()
+    rc = lib().dvo_decode_cmds(_ptr(d), d.size, _ptr(out), out_cap, ctypes.byref(n), int(skip_crc), model_rev,
+                               ctypes.byref(cl.c))
+    return rc, out[: min(n.value, out_cap)].tobytes(), cl
 
 
 def encode_raw(data, opts=None):

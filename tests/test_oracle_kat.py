@@ -252,3 +252,73 @@ def test_random_ir_roundtrip(oracle):
         enc = c.encode(o)
         rc, dec = oracle.decode(enc, out_cap=len(raw) + 64)
         assert rc == 0 and dec == raw, seed
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The one compressed stream the reference tree holds (wasm/wasm.html:98-107): whole-bitstream pin of the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _wasm_vector():
+    import json
+    vec = open(os.path.join(GOLD, "ref_wasm_example.divans"), "rb").read()
+    meta = json.load(open(os.path.join(GOLD, "ref_wasm_example.json")))
+    return vec, meta
+
+
+def test_reference_held_stream_fixture_is_the_reference_bytes():
+    # the committed fixture equals what wasm/wasm.html holds (checked whenever the reference tree is mounted)
+    import re
+    vec, meta = _wasm_vector()
+    assert len(vec) == 113 and hashlib.sha256(vec).hexdigest() == meta["divans_sha256"]
+    html = "/root/reference/wasm/wasm.html"
+    if os.path.exists(html):
+        m = re.search(r"_example_dv_file\s*=\s*\[(.*?)\]", open(html).read(), re.S)
+        assert bytes(int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]{2})", m.group(1))) == vec
+
+
+def test_reference_held_stream_decodes_under_its_model_revision(oracle):
+    vec, meta = _wasm_vector()
+    # container: magic, window 22, two records, EOF marker, CRC32C(header..marker) LE32, "ans~"
+    assert vec[:6] == bytes([0xff, 0xe5, 0x8c, 0x9f, 0x00, 0x16]) and vec[-4:] == b"ans~"
+    assert oracle.crc32c(vec[:-8]) == int.from_bytes(vec[-8:-4], "little")
+    cmd, lit = oracle.demux(vec)
+    assert (len(cmd), len(lit)) == (44, 36)
+    rc, plain, cmds = oracle.decode_cmds(vec, model_rev=oracle.MODEL_WASM_2018)   # CRC checked (skip_crc=False)
+    assert rc == oracle.SUCCESS
+    assert plain == b"It snowed, rained, and hailed the same morning.\n" * 7
+    assert plain.decode("ascii") == meta["plain_text"] and hashlib.sha256(plain).hexdigest() == meta["plain_sha256"]
+    # 9 commands: PredictionMode (UTF8, empty context maps, 8192 x mixing value 4), a literal block switch, literals of
+    # 15 / 11 / 2 bytes, copy(distance 8, 4 bytes), two dictionary words, copy(distance 48, 288 bytes): rANS, CDF arithmetic,
+    # command / literal / copy / dictionary / block-switch coding, the RFC 7932 dictionary, mux framing and CRC32C are
+    # all exercised by this stream.
+    assert cmds.n_cmds == meta["n_cmds"] == 9 and cmds.window == 22
+
+
+def test_reference_held_stream_is_reproduced_by_the_encoder(oracle):
+    # the encoder half: same commands, same options (use_context_map=0 -> mixing values 4, no maps; mixing nibble 0)
+    # -> the reference encoder's own 113 bytes, byte for byte (both rANS payloads, record framing, CRC)
+    vec, _ = _wasm_vector()
+    rc, plain, cmds = oracle.decode_cmds(vec, model_rev=oracle.MODEL_WASM_2018)
+    assert rc == 0
+    enc = cmds.encode(oracle.options(window_size=22, use_context_map=0, dynamic_context_mixing=0, model_rev=oracle.MODEL_WASM_2018))
+    assert enc == vec
+
+
+def test_reference_held_stream_version_skew_is_exactly_two_constructs(oracle):
+    # Under the model of the mounted source tree the stream does NOT decode: command nibbles 1..20 agree (PredictionMode,
+    # UTF8, mixing 0, depth 0, MUD x4), nibble 21 (first context-map mnemonic, codec/context_map.rs:273) is coded with
+    # PredictionModePriorType::Mnemonic's own fresh slot today (codec/priors.rs:130) -- the stream needs the slot shared by
+    # DynamicContextMixingSpeed/PriorDepth/ContextMapSpeedPalette[0]; and mixing values >= 256 use value[i-256] as prior
+    # today (context_map.rs:395-399) -- the stream uses slot 16 throughout.
+    vec, _ = _wasm_vector()
+    rc, plain = oracle.decode(vec)
+    assert rc == oracle.NEEDS_MORE_INPUT and plain == b""
+    # the same commands under today's model round-trip, and differ from the 2018 stream only in the command coder's bytes
+    rc, plain, cmds = oracle.decode_cmds(vec, model_rev=oracle.MODEL_WASM_2018)
+    now = cmds.encode(oracle.options(window_size=22, use_context_map=0, dynamic_context_mixing=0))
+    rc2, plain2 = oracle.decode(now)
+    assert rc2 == 0 and plain2 == plain
+    assert oracle.demux(now)[1] == oracle.demux(vec)[1]      # literal coder payload: identical
+    assert oracle.demux(now)[0] != oracle.demux(vec)[0]      # command coder payload: the PredictionMode priors differ
