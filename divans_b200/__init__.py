@@ -173,11 +173,13 @@ class Engine:
         if not self._h:
             raise DivansError("divans_b200_create(device=%d) failed: no usable sm_100a CUDA device (no CPU fallback)" % device)
         self.device = device
+        self._inflight = {}     # ticket -> every buffer the C side still reads or writes for that pipelined batch
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.divans_b200_destroy(self._h)
+            self._L.divans_b200_destroy(self._h)   # drains the pipelined batches (their buffers are still referenced here)
             self._h = None
+            self._inflight.clear()
 
     def __del__(self):
         try:
@@ -231,12 +233,17 @@ class Engine:
         if rc != DIVANS_SUCCESS:
             raise DivansError("decode_batch_host_async: " + self._err())
         eng = self
+        # The C side writes out / out_len / status when the batch is retired (wait(), the async call that reuses the lane,
+        # or destroy): the engine itself keeps them alive until then, also when the caller drops the handle.
+        if ticket.value >= 0:
+            eng._inflight[ticket.value] = (keep, in_blob, out, out_len, status)
 
         class _Pending:
             def wait(self_inner):
                 if eng._L.divans_b200_decode_batch_host_wait(eng._h, ticket.value) != DIVANS_SUCCESS:
                     raise DivansError("decode_batch_host_wait: " + eng._err())
-                _ = keep, in_blob, out      # the buffers stay referenced until the batch is complete
+                if eng._inflight.get(ticket.value, (None,) * 5)[3] is out_len:
+                    del eng._inflight[ticket.value]
                 return out_len, status
         return _Pending()
 

@@ -63,6 +63,7 @@ struct divans_b200_ctx {
     uint64_t *d_rcp15 = nullptr;
     bool main_end_is_evm1 = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, evm1 = nullptr;   // ev0 | frame kernel | evm | decode kernel | ev1
+    cudaEvent_t ev_busy = nullptr; bool busy_recorded = false;                 // end of the most recent launch set on any stream
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
     std::string err;
@@ -107,6 +108,7 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
     bool ok = ck(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate") &&
               ck(ctx, cudaEventCreate(&ctx->ev0), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->ev1), "cudaEventCreate") &&
               ck(ctx, cudaEventCreate(&ctx->evm), "cudaEventCreate") && ck(ctx, cudaEventCreate(&ctx->evm1), "cudaEventCreate") &&
+              ck(ctx, cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming), "cudaEventCreate") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_tables, TB_TOTAL), "cudaMalloc(tables)") &&
               ck(ctx, cudaMemcpy(ctx->d_tables, dv_tables_blob, TB_TOTAL, cudaMemcpyHostToDevice), "cudaMemcpy(tables)") &&
               ck(ctx, cudaMalloc((void **)&ctx->d_counter, 64), "cudaMalloc(counter)") &&
@@ -129,13 +131,17 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
 extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (int t = 0; t < 2; t++) divans_b200_decode_batch_host_wait(ctx, t);   // in-flight pipelined batches still write caller memory
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
     cudaFree(ctx->d_arena); cudaFree(ctx->d_tables); cudaFree(ctx->d_counter); cudaFree(ctx->d_nibbles);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_payload); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->evm) cudaEventDestroy(ctx->evm);
     if (ctx->evm1) cudaEventDestroy(ctx->evm1);
+    if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
     cudaFree(ctx->d_sf); cudaFree(ctx->d_replay); cudaFree(ctx->d_enc_scratch); cudaFree(ctx->d_pm_internal); cudaFree(ctx->d_rcp15);
     for (auto &ln : ctx->lane) {
         cudaFree(ln.d_in); cudaFree(ln.d_out); cudaFree(ln.d_meta);
@@ -177,15 +183,17 @@ static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
     return DIVANS_SUCCESS;
 }
 
-extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
-                                                        const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
-                                                        const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
-                                                        uint64_t in_total_bytes, uint32_t flags, void *cuda_stream) {
-    if (!ctx) return DIVANS_FAILURE;
-    if (n == 0) return DIVANS_SUCCESS;
+// One context = one set of scratch buffers (work counter, frame table, compacted payload, arena slots, timing events):
+// launches of different calls must not overlap on the GPU.  Calls are serialised on the host by ctx->mu and on the device
+// by `ev_busy`: a launch set on any stream first waits for the previous call's last kernel.
+static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                         const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
+                                         const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
+                                         uint64_t in_total_bytes, uint32_t flags, void *cuda_stream) {
     if (n > 0xffffffffull) { ctx->err = "too many streams"; return DIVANS_FAILURE; }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (ctx->busy_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
     uint32_t gpb = DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
     uint32_t resident = (uint32_t)(n < ctx->max_resident ? n : ctx->max_resident);
     uint32_t blocks = (resident + gpb - 1) / gpb;
@@ -204,16 +212,26 @@ extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, si
     static const bool dbg = getenv("DIVANS_B200_DEBUG") != nullptr;
     static const bool skip_decode = getenv("DIVANS_B200_SKIP_DECODE") != nullptr;
     CK(cudaEventRecord(ctx->ev0, st));
-    launch_frame(fp, ctx->d_payload, st);
+    launch_frame(fp, ctx->d_payload, (uint64_t)ctx->payload_cap, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
     if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;
     ctx->main_end_is_evm1 = false;
     ctx->launches += skip_decode ? 3 : 4;
     CK(cudaGetLastError());
     return DIVANS_SUCCESS;
+}
+extern "C" DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                                                        const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
+                                                        const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,
+                                                        uint64_t in_total_bytes, uint32_t flags, void *cuda_stream) {
+    if (!ctx) return DIVANS_FAILURE;
+    if (n == 0) return DIVANS_SUCCESS;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return decode_device_nolock(ctx, n, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status, in_total_bytes, flags, cuda_stream);
 }
 
 extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
@@ -224,10 +242,11 @@ extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     // extent of the input / output blobs
-    uint64_t in_end = 0, out_end = 0;
+    uint64_t in_end = 0, out_end = 0, in_sum = 0;
     for (size_t i = 0; i < n; i++) {
         if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
         if (out_off[i] + out_cap[i] > out_end) out_end = out_off[i] + out_cap[i];
+        in_sum += in_len[i];                       // input regions may alias (the same stream decoded n times)
     }
     if (!grow(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)in_end + 64)) return DIVANS_FAILURE;
     if (!grow(ctx, &ctx->d_out, &ctx->d_out_cap, (size_t)out_end + 64)) return DIVANS_FAILURE;
@@ -240,18 +259,23 @@ extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size
     CK(cudaMemcpyAsync(m + 2 * n, out_off, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m + 3 * n, out_cap, n * 8, cudaMemcpyHostToDevice, st));
     int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
-    DivansResult r = divans_b200_decode_batch_device(ctx, n, ctx->d_in, m, m + n, ctx->d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
-                                                     in_end, flags, st);
+    DivansResult r = decode_device_nolock(ctx, n, ctx->d_in, m, m + n, ctx->d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
+                                          in_sum > in_end ? in_sum : in_end, flags, st);
     if (r != DIVANS_SUCCESS) return r;
     CK(cudaMemcpyAsync(out_len, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // copy back only what was produced (contiguous runs are merged into one transfer)
+    // Copy back only what was produced, and never outside a declared region out[out_off[i] .. +out_cap[i]): consecutive
+    // streams whose regions are exactly adjacent AND completely filled share one transfer; the run ends with the first
+    // stream that left room in its region.
     size_t i = 0;
     while (i < n) {
-        uint64_t lo = out_off[i], hi = out_off[i] + out_len[i];
+        const uint64_t lo = out_off[i];
+        uint64_t hi = lo + (out_len[i] < out_cap[i] ? out_len[i] : out_cap[i]);
         size_t j = i + 1;
-        while (j < n && out_off[j] >= lo && out_off[j] <= hi + 4096) { uint64_t e = out_off[j] + out_len[j]; if (e > hi) hi = e; j++; }
+        while (j < n && out_len[j - 1] >= out_cap[j - 1] && out_off[j] == out_off[j - 1] + out_cap[j - 1]) {
+            hi = out_off[j] + (out_len[j] < out_cap[j] ? out_len[j] : out_cap[j]); j++;
+        }
         if (hi > lo) CK(cudaMemcpyAsync(out + lo, ctx->d_out + lo, hi - lo, cudaMemcpyDeviceToHost, st));
         i = j;
     }
@@ -265,31 +289,32 @@ extern "C" void divans_b200_encode_options_default(divans_b200_encode_options *o
     o->literal_pred_mode = 0; o->literal_mixing_value = 4;
 }
 // ---- pipelined host-buffer decode: H2D of batch k+1 and D2H of batch k-1 overlap the kernels of batch k ----
-extern "C" DivansResult divans_b200_decode_batch_host_wait(divans_b200_ctx *ctx, int32_t ticket) {
-    if (!ctx || ticket < 0 || ticket > 1) return DIVANS_FAILURE;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    divans_b200_ctx::Lane &ln = ctx->lane[ticket];
+static DivansResult lane_wait_nolock(divans_b200_ctx *ctx, int t) {
+    divans_b200_ctx::Lane &ln = ctx->lane[t];
     if (!ln.pending) return DIVANS_SUCCESS;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ln.e_out));
     memcpy(ln.u_out_len, ln.h_res, ln.n * 8);
     memcpy(ln.u_status, ln.h_res + ln.n * 8, ln.n * 4);
-    ln.pending = false;
+    ln.pending = false; ln.u_out_len = nullptr; ln.u_status = nullptr;
     return DIVANS_SUCCESS;
+}
+extern "C" DivansResult divans_b200_decode_batch_host_wait(divans_b200_ctx *ctx, int32_t ticket) {
+    if (!ctx) return DIVANS_FAILURE;
+    if (ticket == DIVANS_B200_TICKET_EMPTY) return DIVANS_SUCCESS;   // an empty batch holds no lane
+    if (ticket < 0 || ticket > 1) return DIVANS_FAILURE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return lane_wait_nolock(ctx, ticket);
 }
 extern "C" DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
                                                             const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                                             const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags,
                                                             int32_t *ticket) {
     if (!ctx || !ticket) return DIVANS_FAILURE;
-    if (n == 0) { *ticket = 0; return DIVANS_SUCCESS; }
-    int t;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        t = (int)(ctx->async_seq++ & 1);
-    }
-    if (ctx->lane[t].pending && divans_b200_decode_batch_host_wait(ctx, t) != DIVANS_SUCCESS) return DIVANS_FAILURE;
+    if (n == 0) { *ticket = DIVANS_B200_TICKET_EMPTY; return DIVANS_SUCCESS; }
     std::lock_guard<std::mutex> lk(ctx->mu);
+    const int t = (int)(ctx->async_seq++ & 1);
+    if (lane_wait_nolock(ctx, t) != DIVANS_SUCCESS) return DIVANS_FAILURE;   // a third batch first retires the oldest one
     CK(cudaSetDevice(ctx->device));
     divans_b200_ctx::Lane &ln = ctx->lane[t];
     if (!ctx->s_h2d) { CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)); }
@@ -297,11 +322,12 @@ extern "C" DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx
         CK(cudaEventCreateWithFlags(&ln.e_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ln.e_k, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.e_out, cudaEventDisableTiming));
     }
-    uint64_t in_end = 0, out_lo = ~0ull, out_hi = 0;
+    uint64_t in_end = 0, in_sum = 0, out_lo = ~0ull, out_hi = 0;
     for (size_t i = 0; i < n; i++) {
         if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
         if (out_off[i] < out_lo) out_lo = out_off[i];
         if (out_off[i] + out_cap[i] > out_hi) out_hi = out_off[i] + out_cap[i];
+        in_sum += in_len[i];
     }
     // (re)allocation of a lane's buffers synchronises the device: only while the pipeline warms up
     if (!grow(ctx, &ln.d_in, &ln.d_in_cap, (size_t)in_end + 64)) return DIVANS_FAILURE;
@@ -323,14 +349,24 @@ extern "C" DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx
     CK(cudaEventRecord(ln.e_in, ctx->s_h2d));
     CK(cudaStreamWaitEvent(ctx->stream, ln.e_in, 0));
     int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
-    DivansResult r = divans_b200_decode_batch_device(ctx, n, ln.d_in, m, m + n, ln.d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status, in_end,
-                                                     flags, ctx->stream);
+    // the regions are copied back whole (out_len is not known yet): zero them first so that the bytes past out_len are
+    // zeros, not plaintext of an earlier batch
+    if (out_hi > out_lo) CK(cudaMemsetAsync(ln.d_out + out_lo, 0, out_hi - out_lo, ctx->stream));
+    DivansResult r = decode_device_nolock(ctx, n, ln.d_in, m, m + n, ln.d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
+                                          in_sum > in_end ? in_sum : in_end, flags, ctx->stream);
     if (r != DIVANS_SUCCESS) return r;
     CK(cudaEventRecord(ln.e_k, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ln.e_k, 0));
     CK(cudaMemcpyAsync(ln.h_res, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
     CK(cudaMemcpyAsync(ln.h_res + n * 8, d_status, n * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    if (out_hi > out_lo) CK(cudaMemcpyAsync(out + out_lo, ln.d_out + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    // one transfer per run of exactly adjacent regions: nothing outside out[out_off[i] .. +out_cap[i]) is written
+    for (size_t i = 0; i < n;) {
+        const uint64_t lo = out_off[i]; uint64_t hi = lo + out_cap[i];
+        size_t j = i + 1;
+        while (j < n && out_off[j] == hi) { hi += out_cap[j]; j++; }
+        if (hi > lo) CK(cudaMemcpyAsync(out + lo, ln.d_out + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        i = j;
+    }
     CK(cudaEventRecord(ln.e_out, ctx->s_d2h));
     ln.pending = true;
     *ticket = t;
@@ -395,6 +431,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     ep.use_context_map = o->use_context_map; ep.force_stride = o->force_stride; ep.have_literal_adaptation = o->have_literal_adaptation;
     for (int k = 0; k < 4; k++) ep.literal_adaptation[k] = pack_speed(o->literal_adaptation[k]);
     ep.model_rev = o->model_rev == DIVANS_B200_MODEL_WASM_2018 ? 1 : 0;
+    if (ctx->busy_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
     CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
     CK(cudaEventRecord(ctx->ev0, st));
     CK(cudaEventRecord(ctx->evm, st));
@@ -402,6 +439,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     CK(cudaEventRecord(ctx->evm1, st));
     launch_encode_flush_mux(ep, st);
     CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;
     ctx->main_end_is_evm1 = true;
     ctx->launches += 4;
     CK(cudaGetLastError());
@@ -417,6 +455,7 @@ extern "C" DivansResult divans_b200_encode_batch_device(divans_b200_ctx *ctx, si
     if (!ctx || !opts) return DIVANS_FAILURE;
     if (n == 0) return DIVANS_SUCCESS;
     if (n > 0xffffffffull || max_in_len > 0x7fff0000ull) { ctx->err = "batch too large"; return DIVANS_FAILURE; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     int window = opts->window_size < 10 ? 10 : (opts->window_size > 24 ? 24 : opts->window_size);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
@@ -550,12 +589,36 @@ struct HostAlloc {   // CAllocator or malloc (ffi/alloc_util.rs:70-99: memory is
     void free(void *p) { if (!p) return; if (a.free_func) a.free_func(a.opaque, p); else ::free(p); }
 };
 
+// Growable byte buffer whose storage comes from the state's allocator (the reference routes every allocation through the
+// CAllocator, ffi/alloc_util.rs:70-99: a NO_MALLOC client -- c/custom_alloc.h -- must never see a malloc from us).
+// Growth is geometric and frees the old block after the copy; a bump arena that only reclaims LIFO still bounds the total at
+// about 3x the final size.
+struct ByteBuf {
+    HostAlloc *al = nullptr; uint8_t *p = nullptr; size_t n = 0, cap = 0;
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t nc = cap ? cap : 4096;
+        while (nc < want) { if (nc > ((size_t)1 << 62)) return false; nc *= 2; }
+        uint8_t *q = (uint8_t *)al->alloc(nc);
+        if (!q) return false;
+        if (n) memcpy(q, p, n);
+        al->free(p); p = q; cap = nc;
+        return true;
+    }
+    bool append(const uint8_t *src, size_t m) { if (!reserve(n + m)) return false; if (m) memcpy(p + n, src, m); n += m; return true; }
+    bool resize(size_t m) { if (!reserve(m)) return false; n = m; return true; }
+    void release() { al->free(p); p = nullptr; n = cap = 0; }
+    size_t size() const { return n; }
+    uint8_t *data() { return p; }
+    uint8_t operator[](size_t i) const { return p[i]; }
+};
+
 struct DivansDecompressorState {
     HostAlloc al;
     bool self_in_custom = false;
     uint8_t skip_crc = 0;
-    std::vector<uint8_t> *inbuf = nullptr;    // buffered compressed stream
-    std::vector<uint8_t> *outbuf = nullptr;   // decoded stream waiting to be handed out
+    ByteBuf inbuf;                            // buffered compressed stream
+    ByteBuf outbuf;                           // decoded stream waiting to be handed out
     size_t out_cursor = 0;
     // incremental framing scan (host): how far the record chain has been walked
     size_t scan_pos = 16; bool saw_eof = false; size_t total_len = 0; bool decoded = false; bool failed = false;
@@ -570,7 +633,7 @@ static DivansDecompressorState *new_decomp(CAllocator a, uint8_t skip_crc) {
         s->self_in_custom = true;
     } else s = new DivansDecompressorState();
     s->al.a = a; s->skip_crc = skip_crc;
-    s->inbuf = new std::vector<uint8_t>(); s->outbuf = new std::vector<uint8_t>();
+    s->inbuf.al = &s->al; s->outbuf.al = &s->al;
     if (!shared_ctx()) { s->failed = true; }
     return s;
 }
@@ -581,7 +644,7 @@ extern "C" DivansDecompressorState *divans_new_decompressor_with_custom_alloc(CA
 }
 extern "C" void divans_free_decompressor(DivansDecompressorState *s) {
     if (!s) return;
-    delete s->inbuf; delete s->outbuf;
+    s->outbuf.release(); s->inbuf.release();
     if (s->self_in_custom) { HostAlloc al = s->al; s->~DivansDecompressorState(); al.free(s); }
     else delete s;
 }
@@ -592,7 +655,7 @@ extern "C" void divans_decompressor_free_usize(DivansDecompressorState *s, size_
 
 // walk record headers over what has been buffered so far; sets saw_eof/total_len once the EOF marker is visible
 static int scan_frames(DivansDecompressorState *s) {
-    const std::vector<uint8_t> &b = *s->inbuf;
+    const ByteBuf &b = s->inbuf;
     if (b.size() < 16) return 0;
     if (b[0] != 0xff || b[1] != 0xe5 || b[2] != 0x8c || b[3] != 0x9f) return -1;
     if (b[5] < 10 || b[5] >= 25) return -1;
@@ -622,46 +685,51 @@ extern "C" DivansResult divans_decode(DivansDecompressorState *s, const uint8_t 
         // take input until the whole stream (through the 8-byte trailer) is buffered
         while (*input_offset < input_size) {
             size_t want;
-            if (s->saw_eof) want = s->total_len - s->inbuf->size();
+            if (s->saw_eof) want = s->total_len - s->inbuf.size();
             else {
-                size_t have = s->inbuf->size();
+                size_t have = s->inbuf.size();
                 size_t target = have < 16 ? 16 : (s->scan_pos + 3 > have ? s->scan_pos + 3 : have + 1);
                 want = target - have;
             }
             if (want == 0) break;
             size_t avail = input_size - *input_offset;
             size_t take = want < avail ? want : avail;
-            s->inbuf->insert(s->inbuf->end(), input_buf_ptr + *input_offset, input_buf_ptr + *input_offset + take);
+            if (!s->inbuf.append(input_buf_ptr + *input_offset, take)) { s->failed = true; return DIVANS_FAILURE; }
             *input_offset += take;
             int sc = scan_frames(s);
             if (sc < 0) { s->failed = true; return DIVANS_FAILURE; }
-            if (s->saw_eof && s->inbuf->size() >= s->total_len) break;
+            if (s->saw_eof && s->inbuf.size() >= s->total_len) break;
         }
-        if (!(s->saw_eof && s->inbuf->size() >= s->total_len)) return DIVANS_NEEDS_MORE_INPUT;
+        if (!(s->saw_eof && s->inbuf.size() >= s->total_len)) return DIVANS_NEEDS_MORE_INPUT;
         divans_b200_ctx *ctx = shared_ctx();
         if (!ctx) { s->failed = true; return DIVANS_FAILURE; }
-        // output size is not in the header: start from a guess, double on NEEDS_MORE_OUTPUT
-        size_t cap = s->inbuf->size() * 8 + (1 << 16);
+        // The output size is not in the header: start from a guess and grow on NEEDS_MORE_OUTPUT.  Growth is bounded by the
+        // largest output a divANS stream of this size can describe per coded nibble (a copy command of 2^24 - 1 bytes
+        // costs >= 3 nibbles of the command coder), by DIVANS_B200_MAX_OUTPUT (default 2^32) and by what the allocator
+        // hands out: a decompression bomb ends in DIVANS_FAILURE, not in an exception crossing the C boundary.
+        static const size_t max_out = []() { const char *e = getenv("DIVANS_B200_MAX_OUTPUT"); return e ? (size_t)strtoull(e, nullptr, 0) : ((size_t)1 << 32); }();
+        size_t cap = s->inbuf.size() * 8 + (1 << 16);
         for (;;) {
-            s->outbuf->resize(cap);
-            uint64_t in_off = 0, in_len = s->inbuf->size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
-            DivansResult r = divans_b200_decode_batch_host(ctx, 1, s->inbuf->data(), &in_off, &in_len, s->outbuf->data(), &out_off, &out_cap,
+            if (cap > max_out) cap = max_out;
+            if (!s->outbuf.resize(cap)) { s->failed = true; return DIVANS_FAILURE; }
+            uint64_t in_off = 0, in_len = s->inbuf.size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
+            DivansResult r = divans_b200_decode_batch_host(ctx, 1, s->inbuf.data(), &in_off, &in_len, s->outbuf.data(), &out_off, &out_cap,
                                                            &out_len, &status, s->skip_crc ? DIVANS_B200_FLAG_SKIP_CRC : 0);
             if (r != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
-            if (status == DIVANS_NEEDS_MORE_OUTPUT && cap < ((size_t)1 << 34)) { cap *= 4; continue; }
+            if (status == DIVANS_NEEDS_MORE_OUTPUT && cap < max_out) { s->outbuf.release(); cap *= 4; continue; }
             if (status != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
-            s->outbuf->resize(out_len);
+            s->outbuf.n = out_len;
             break;
         }
         s->decoded = true;
-        std::vector<uint8_t>().swap(*s->inbuf);
+        // (the input buffer is kept until free: a LIFO arena could not reclaim it from under the output buffer anyway)
     }
-    size_t remaining = s->outbuf->size() - s->out_cursor;
+    size_t remaining = s->outbuf.size() - s->out_cursor;
     size_t room = output_size - *output_offset;
     size_t give = remaining < room ? remaining : room;
-    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf->data() + s->out_cursor, give);
+    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf.data() + s->out_cursor, give);
     s->out_cursor += give; *output_offset += give;
-    return s->out_cursor == s->outbuf->size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
+    return s->out_cursor == s->outbuf.size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
 }
 
 // ---- compressor side ----
@@ -671,7 +739,7 @@ struct DivansCompressorState {
     divans_b200_encode_options opts;
     int use_brotli = 1;
     bool started = false, flushed = false, failed = false;
-    std::vector<uint8_t> *inbuf = nullptr, *outbuf = nullptr;
+    ByteBuf inbuf, outbuf;
     size_t out_cursor = 0;
 };
 extern "C" DivansCompressorState *divans_new_compressor_with_custom_alloc(CAllocator a) {
@@ -684,13 +752,13 @@ extern "C" DivansCompressorState *divans_new_compressor_with_custom_alloc(CAlloc
     s->al.a = a;
     divans_b200_encode_options_default(&s->opts);
     s->opts.dynamic_context_mixing = 1;   // DivansCompressorOptions::default(), src/interface.rs:462-484
-    s->inbuf = new std::vector<uint8_t>(); s->outbuf = new std::vector<uint8_t>();
+    s->inbuf.al = &s->al; s->outbuf.al = &s->al;
     return s;
 }
 extern "C" DivansCompressorState *divans_new_compressor(void) { return divans_new_compressor_with_custom_alloc(CAllocator{nullptr, nullptr, nullptr}); }
 extern "C" void divans_free_compressor(DivansCompressorState *s) {
     if (!s) return;
-    delete s->inbuf; delete s->outbuf;
+    s->outbuf.release(); s->inbuf.release();
     if (s->self_in_custom) { HostAlloc al = s->al; s->~DivansCompressorState(); al.free(s); }
     else delete s;
 }
@@ -736,7 +804,7 @@ extern "C" DivansResult divans_encode(DivansCompressorState *s, const uint8_t *i
     if (!s || !input_offset || !output_offset) return DIVANS_FAILURE;
     if (s->failed || s->flushed) return DIVANS_FAILURE;
     s->started = true;
-    s->inbuf->insert(s->inbuf->end(), input_buf_ptr + *input_offset, input_buf_ptr + input_size);
+    if (!s->inbuf.append(input_buf_ptr + *input_offset, input_size - *input_offset)) { s->failed = true; return DIVANS_FAILURE; }
     *input_offset = input_size;
     return DIVANS_NEEDS_MORE_INPUT;   // like the reference: all input consumed, nothing is "done" before flush
 }
@@ -747,18 +815,19 @@ extern "C" DivansResult divans_encode_flush(DivansCompressorState *s, uint8_t *o
     if (!s->flushed) {
         divans_b200_ctx *ctx = shared_ctx();
         if (!ctx) { s->failed = true; return DIVANS_FAILURE; }
-        size_t cap = s->inbuf->size() + s->inbuf->size() / 2 + 70000;
-        s->outbuf->resize(cap);
-        uint64_t in_off = 0, in_len = s->inbuf->size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
-        DivansResult r = divans_b200_encode_batch_host(ctx, 1, s->inbuf->data(), &in_off, &in_len, s->outbuf->data(), &out_off, &out_cap, &out_len,
+        size_t cap = s->inbuf.size() + s->inbuf.size() / 2 + 70000;
+        if (!s->outbuf.resize(cap)) { s->failed = true; return DIVANS_FAILURE; }
+        uint64_t in_off = 0, in_len = s->inbuf.size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
+        static const uint8_t none = 0;
+        DivansResult r = divans_b200_encode_batch_host(ctx, 1, in_len ? s->inbuf.data() : &none, &in_off, &in_len, s->outbuf.data(), &out_off, &out_cap, &out_len,
                                                        &status, &s->opts);
         if (r != DIVANS_SUCCESS || status != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
-        s->outbuf->resize(out_len);
+        s->outbuf.n = out_len;
         s->flushed = true;
     }
-    size_t remaining = s->outbuf->size() - s->out_cursor, room = output_size - *output_offset;
+    size_t remaining = s->outbuf.size() - s->out_cursor, room = output_size - *output_offset;
     size_t give = remaining < room ? remaining : room;
-    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf->data() + s->out_cursor, give);
+    if (give) memcpy(output_buf_ptr + *output_offset, s->outbuf.data() + s->out_cursor, give);
     s->out_cursor += give; *output_offset += give;
-    return s->out_cursor == s->outbuf->size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
+    return s->out_cursor == s->outbuf.size() ? DIVANS_SUCCESS : DIVANS_NEEDS_MORE_OUTPUT;
 }

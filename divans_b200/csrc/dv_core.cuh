@@ -191,7 +191,7 @@ template <bool ENC, int LPS>
 __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const bool writer) {
     uint32_t n = s.lit_left;
     if (LPS == 16) n = min(n, __shfl_xor_sync(FULL, n, 16));
-    const bool simple = __all_sync(FULL, !s.mixing_trait && s.lit_cfg >= 0);
+    const bool simple = __all_sync(FULL, !s.mixing_trait && s.lit_cfg >= 0 && s.speeds_small);
     if (simple) {
         const int cfg = s.lit_cfg;
         const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;
@@ -243,8 +243,8 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
             //   search(hi) -> load(lo) -> finish(hi) -> search(lo) -> context -> load(next hi) -> finish(lo)
             // The high and low tables never alias, so the early loads cannot overtake a store to the same CDF; the
             // __syncwarp()s order each store against the next load of the same table across lanes.
-            // Adaptive values stay below 2^15 for every speed an encoder can select (limit <= 0x4000 + increment), so the
-            // loop uses plain 32-bit arithmetic where the reference wraps i16.
+            // The loop uses plain 32-bit arithmetic where the reference wraps i16: only entered when speeds_small says no
+            // adaptive value can leave [0, 0x7fff] (dv_engine.cuh: speed_is_small).
             char *ph = hi_tab + (ctx * 256u + ((uint32_t)(l8 >> sh) & mm & (~o1 & 0xffu))) * scale;
             __syncwarp();
             int ch = ld_s16(ph + 2 * g.l16), mh = ld_s16(ph + 30);
@@ -325,7 +325,7 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         enter_lit_nibble<ENC, true>(s, nx);
         return;
     }
-    if (__all_sync(FULL, s.mixing_trait && s.lit_cfg >= 0)) {
+    if (__all_sync(FULL, s.mixing_trait && s.lit_cfg >= 0 && s.speeds_small)) {
         // every group mixes the stride prior with the context-map prior, one mixing-mask value for the whole map
         const int cfg = s.lit_cfg;
         const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xffu : 0u;

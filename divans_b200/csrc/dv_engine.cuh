@@ -113,6 +113,7 @@ struct St {
     uint32_t btype_last, pred_mode;
     int ad_stride;                           // literal_adaptation[0] packed
     bool mixing_trait;
+    bool speeds_small;                       // every literal speed keeps adaptive values inside i16 (see speed_is_small)
     int lit_cfg;                             // >= 0: every mixing-mask entry is equal and this is its mm_cfg() (skip the table read)
     uint8_t *out;                            // output window
     uint32_t out_pos;
@@ -314,6 +315,15 @@ __device__ __forceinline__ uint32_t u8_to_speed_u16(uint32_t data) {
 __device__ __forceinline__ int f8_pair_to_speed(uint32_t a, uint32_t b) {   // nibbles -> stored f8 -> Speed::from_f8_tuple
     uint32_t ra = speed_to_u8_u16(u8_to_speed_u16(a)), rb = speed_to_u8_u16(u8_to_speed_u16(b));
     return sp_pack(u8_to_speed(ra), u8_to_speed(rb));
+}
+
+// The literal fast loops adapt in plain 32-bit arithmetic; the reference wraps i16 (frequentist_cdf.rs:74-85).  The two agree
+// as long as no adaptive value can leave [0, 0x7fff]: a value is at most lim - 1 + inc before a rescale and
+// 3/4 * (value + 16) after one.  Speeds are carried by the stream (f8: up to 30720), so streams whose speeds could wrap
+// take the generic core, which keeps the i16 wrap.
+__device__ __forceinline__ bool speed_is_small(int packed) {
+    const int inc = (int)(short)(packed & 0xffff), lim = packed >> 16;
+    return inc >= 0 && lim >= 0 && lim + inc + 16 <= 0x7fff && 4 * (inc + 16) <= 0x7fff;
 }
 
 // context-map LRU-13 held as 13 bytes in two registers (codec/interface.rs:439-453)

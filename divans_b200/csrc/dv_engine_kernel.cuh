@@ -484,6 +484,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             s.ad_stride = f8_pair_to_speed((uint32_t)a & 0xff, (uint32_t)(a >> 8) & 0xff);
             s.c->ad_cm_lo = f8_pair_to_speed((uint32_t)(a >> 32) & 0xff, (uint32_t)(a >> 40) & 0xff);
             s.c->ad_cm_hi = f8_pair_to_speed((uint32_t)(a >> 48) & 0xff, (uint32_t)(a >> 56) & 0xff);
+            s.speeds_small = speed_is_small(s.ad_stride) && speed_is_small(s.c->ad_cm_lo) && speed_is_small(s.c->ad_cm_hi);
             s.c->lit_slabs_ready = false;
             if (ENC) s.c->in.pos++;
             enter_cmd_type<ENC>(s, nx);
@@ -505,6 +506,7 @@ __device__ __forceinline__ void st_reset(St &s) {
                        // unobservable when a PredictionMode command precedes the first literal
     s.ad_stride = s.c->ad_cm_lo = s.c->ad_cm_hi = SPK_MUD;
     s.c->w_lo.w0 = s.c->w_lo.w1 = 1; s.c->w_lo.norm = 1 << 14; s.c->w_hi = s.c->w_lo;
+    s.speeds_small = true;   // MUD
     s.c->mixing_param = 1; s.mixing_trait = false; s.c->lit_slabs_ready = false; s.lit_cfg = -1;
     s.status = ST_OK; s.c->cur_is_lit = false;
     s.f0 = s.f1 = s.f2 = s.f3 = 0; s.lit_left = s.lit_ctx = s.lit_h = 0;

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(128) frame_kernel(FrameParams p) {
 }
 
 // exclusive scan of the per-stream payload footprints -> frame[4i+3] = base of stream i's compacted payload (16-byte units)
-__global__ void __launch_bounds__(1024) payload_scan_kernel(uint32_t *frame, uint32_t n) {
+// A stream whose compacted payload would not fit the payload buffer (`cap16` 16-byte units: aliased / overlapping input
+// regions, or an underestimated in_total_bytes) is failed here instead of letting the demux kernel write past the end.
+__global__ void __launch_bounds__(1024) payload_scan_kernel(uint32_t *frame, uint32_t n, int32_t *status, uint64_t cap16) {
     __shared__ uint32_t part[1024];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (n + 1023) / 1024;
@@ -98,8 +100,12 @@ __global__ void __launch_bounds__(1024) payload_scan_kernel(uint32_t *frame, uin
     }
     uint32_t base = part[t] - sum;
     for (uint32_t i = lo; i < hi; i++) {
-        frame[4 * i + 3] = base;
-        base += ((frame[4 * i + 1] + 15) >> 4) + ((frame[4 * i + 2] + 15) >> 4) + 1;
+        const uint32_t need = ((frame[4 * i + 1] + 15) >> 4) + ((frame[4 * i + 2] + 15) >> 4) + 1;
+        if ((uint64_t)base + need > cap16) {
+            if (status[i] == ST_OK) status[i] = ST_FAIL;
+            frame[4 * i + 1] = 0; frame[4 * i + 2] = 0; frame[4 * i + 3] = 0;
+        } else frame[4 * i + 3] = base;
+        base += need;
     }
 }
 
@@ -235,10 +241,10 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
 }
 
 #if DV_LPS == 32
-void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st) {
+void launch_frame(const FrameParams &p, uint8_t *payload, uint64_t payload_cap_bytes, cudaStream_t st) {
     uint32_t blocks = (p.n_streams + 3) / 4;   // one warp per stream
     frame_kernel<<<blocks, 128, 0, st>>>(p);
-    payload_scan_kernel<<<1, 1024, 0, st>>>(p.frame, p.n_streams);
+    payload_scan_kernel<<<1, 1024, 0, st>>>(p.frame, p.n_streams, p.status, payload_cap_bytes / 16);
     demux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p, payload);
 }
 #endif

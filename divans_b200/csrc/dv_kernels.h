@@ -5,7 +5,7 @@
 namespace dv {
 constexpr int DECODE_BLOCK_THREADS = 64;
 
-void launch_frame(const FrameParams &p, uint8_t *payload, cudaStream_t st);   // frame + payload scan + demux (3 launches)
+void launch_frame(const FrameParams &p, uint8_t *payload, uint64_t payload_cap_bytes, cudaStream_t st);   // frame + payload scan + demux (3 launches)
 void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 int decode_max_blocks_per_sm32();

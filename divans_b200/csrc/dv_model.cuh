@@ -70,7 +70,25 @@ __device__ __forceinline__ void coder_advance(Coder &k, int start, int freq) {
 // exact floor((c<<15)/max): the reference divides through a reciprocal LUT that is asserted equal to integer
 // division (probability/numeric.rs:26-31, make_div_lut.rs:37-39).  fp32 estimate + integer fix-up: c<<15 has <=16
 // significant bits, so the estimate is within 1 of the true quotient (<= 2^16).
+// The reference's divide, literally (probability/numeric.rs:14-31 with RECIPROCAL[d as u16] = compute_divisor(d),
+// make_div_lut.rs:29-41).  Only reached with operands outside the adaptive range 0 <= c <= max <= 0x7fff, i.e. after a
+// stream-supplied speed made an i16 counter wrap (frequentist_cdf.rs:74-85): there the LUT divide is NOT integer division
+// and the decoder has to reproduce its exact value to stay in step with the reference.
+static __device__ __noinline__ int cdf_div_ref(int c, int maxv) {
+    const uint32_t d = (uint32_t)maxv & 0xffffu;
+    const int32_t num = (int32_t)((uint32_t)c << 15);
+    long long inv = 0; int shift = 0;
+    if (d != 0) {
+        const int bit_len = 32 - __clz((int)d);   // 16 - leading_zeros(u16)
+        inv = ((((long long)1 << bit_len) - (long long)d) << 31) / (long long)d + 1;
+        shift = bit_len - 1;
+    }
+    const long long m = inv * (long long)num;
+    const int32_t t = (int32_t)(m >> 31);
+    return (t + (((int32_t)((long long)num - (m >> 31))) >> 1)) >> shift;
+}
 __device__ __forceinline__ int cdf_div(int c, int maxv) {
+    if (((unsigned)c | (unsigned)(maxv - 1)) > 0x7fffu) return cdf_div_ref(c, maxv);   // wrapped counters (never with the named speeds)
     uint32_t d = (uint32_t)maxv & 0xffffu;
     uint32_t n = (uint32_t)(c << 15);
     float rc;

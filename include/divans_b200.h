@@ -126,7 +126,8 @@ float divans_b200_last_kernel_ms(divans_b200_ctx *ctx);
 float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx);
 
 /* Decode n independent, complete .divans streams held in HOST memory.
- * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]).
+ * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]) and only
+ * out[out_off[i] .. +out_len[i]) is written.  Input regions may alias.
  * Includes H2D of the inputs and D2H of outputs inside the call.  Returns DIVANS_SUCCESS if the batch ran
  * (inspect status[] per stream), DIVANS_FAILURE on CUDA/context errors. */
 DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
@@ -136,16 +137,22 @@ DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const
  * kernels and the D2H copies on the context's copy / compute streams and returns a ticket (0 or 1; at most two batches
  * in flight, a third call first waits for the oldest).  The copies of one batch overlap the kernels of its neighbours.
  * `in` / `out` must stay valid (and should be pinned, else the copies degrade to synchronous ones) until
- * divans_b200_decode_batch_host_wait(ctx, ticket) returns; out_len[] / status[] are filled by the wait call; the whole
- * [min out_off, max out_off + out_cap) range of `out` is written. */
+ * divans_b200_decode_batch_host_wait(ctx, ticket) returns -- out_len[] / status[] too: they are filled by the wait call (or by
+ * the third async call, which retires the oldest batch, or by divans_b200_destroy).  Every region out[out_off[i] .. +out_cap[i])
+ * is written whole (zeros past out_len[i]); nothing outside the regions is touched.  An empty batch (n == 0) returns
+ * DIVANS_B200_TICKET_EMPTY, which wait() accepts as a no-op. */
+#define DIVANS_B200_TICKET_EMPTY (-1)
 DivansResult divans_b200_decode_batch_host_async(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,
                                                  const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                                  const uint64_t *out_cap, uint64_t *out_len, int32_t *status, uint32_t flags,
                                                  int32_t *ticket);
 DivansResult divans_b200_decode_batch_host_wait(divans_b200_ctx *ctx, int32_t ticket);
 /* Same, all pointers are DEVICE pointers (inputs already resident in HBM, outputs left in HBM).
- * `in_total_bytes` = size of the d_in blob (upper bound of sum(in_len)); `cuda_stream` is a cudaStream_t (NULL = the
- * context's own stream).  Asynchronous: returns after enqueueing. */
+ * `in_total_bytes` >= sum(in_len) sizes the compacted-payload scratch (streams that would not fit it are failed with
+ * status 3, never written out of bounds); `cuda_stream` is a cudaStream_t (NULL = the context's own stream).
+ * Asynchronous: returns after enqueueing.  A context owns ONE set of scratch buffers: calls on the same context are
+ * serialised (host mutex + an event that makes each launch set wait for the previous one, whatever stream it is on);
+ * for concurrent batches create one context per batch in flight. */
 DivansResult divans_b200_decode_batch_device(divans_b200_ctx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
                                              const uint64_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
                                              const uint64_t *d_out_cap, uint64_t *d_out_len, int32_t *d_status,

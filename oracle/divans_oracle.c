@@ -346,6 +346,7 @@ static inline void ans_dec_advance(ans_dec *d, int16_t start, int16_t freq) {
 typedef struct {
     uint32_t *sf; size_t n_sf; /* (start | freq<<16) recorded for the current chunk, ans.rs:289-301 */
     bytevec out; uint64_t n_syms;
+    int bad; /* a symbol with frequency <= 0 was put: the reference's flush divides by it (ans.rs:362-366) and panics */
 } ans_enc;
 static void ans_enc_init(ans_enc *e) { memset(e, 0, sizeof(*e)); e->sf = (uint32_t *)malloc(NUM_SYMBOLS_BEFORE_FLUSH * 4); }
 static void ans_enc_free(ans_enc *e) { free(e->sf); bv_free(&e->out); }
@@ -377,6 +378,7 @@ static void ans_enc_flush_chunk(ans_enc *e) {
     e->n_sf = 0;
 }
 static inline void ans_enc_put(ans_enc *e, int16_t start, int16_t freq) {
+    if (freq <= 0) { e->bad = 1; freq = 1; start = 0; } /* only reachable after a stream-supplied speed wrapped an i16 counter */
     e->sf[e->n_sf++] = (uint32_t)(uint16_t)start | ((uint32_t)(uint16_t)freq << 16);
     e->n_syms++;
     if (e->n_sf == NUM_SYMBOLS_BEFORE_FLUSH) ans_enc_flush_chunk(e);
@@ -1233,6 +1235,7 @@ int dvo_encode_cmds(const dvo_cmdlist *l, const dvo_options *o, uint8_t *out, si
         default: rc = DVO_FAILURE;
         }
     }
+    if (rc == DVO_SUCCESS && (s->cmd.e.bad || s->lit.e.bad)) rc = DVO_FAILURE; /* the reference encoder panics here */
     if (rc == DVO_SUCCESS) {
         /* flush: end-of-stream nibble 0xf, close both coders, drain mux, EOF marker, trailer (codec/mod.rs:424-560) */
         code_and_blend(&s->cmd, 0xf, P(s->cc_priors, T_CC, CC_FullSelection, (uint32_t)s->last_4_states >> 4, 0, 0), SPEED_ROCKET);

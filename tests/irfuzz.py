@@ -4,7 +4,11 @@ import ctypes
 import numpy as np
 
 
-def random_ir(oracle, seed, n_cmds=120, window=16, text=None):
+def random_ir(oracle, seed, n_cmds=120, window=16, text=None, wide_speeds=False):
+    """wide_speeds: draw the six literal speeds over the whole f8 range a stream can carry (probability/interface.rs:566-585:
+    up to 30720), not only the named palette -- i16 counters wrap (frequentist_cdf.rs:74-85) and the LUT divide leaves the
+    integer-division regime; such streams are usually not decodable back to their input, but every decoder must walk
+    them identically."""
     rng = np.random.default_rng(seed)
     L = oracle.lib()
     lines = ["window %d 0 0 0" % window]
@@ -30,9 +34,16 @@ def random_ir(oracle, seed, n_cmds=120, window=16, text=None):
             mv = np.where(rng.random(8192) < 0.9, 4, rng.integers(0, 9, 8192))
         s = "prediction %s lcontextmap %s dcontextmap %s mixingvalues %s" % (
             mode, " ".join(map(str, lmap)), " ".join(map(str, dmap)), " ".join(map(str, mv)))
-        if rng.random() < 0.5:
+        if wide_speeds or rng.random() < 0.5:
             sp = [int(x) for x in rng.choice([1, 2, 4, 8, 16, 32, 48, 64, 128, 512], 6)]
             mx = [int(x) for x in rng.choice([128, 1024, 2048, 4096, 8192, 16384], 6)]
+            if wide_speeds:
+                f8 = lambda: min(16384, int(L.dvo_u8_to_speed(int(rng.integers(8, 128)))) & 0xffff)   # the IR grammar caps speeds at 16384 (divans.rs:296)
+                for k in range(6):
+                    if rng.random() < 0.6:
+                        sp[k] = f8()
+                    if rng.random() < 0.6:
+                        mx[k] = f8()
             s += " cmspeedinc %d %d cmspeedmax %d %d stspeedinc %d %d stspeedmax %d %d mxspeedinc %d %d mxspeedmax %d %d" % (
                 sp[0], sp[1], mx[0], mx[1], sp[2], sp[3], mx[2], mx[3], sp[4], sp[5], mx[4], mx[5])
         return s, n_bt
@@ -80,3 +91,11 @@ def random_ir(oracle, seed, n_cmds=120, window=16, text=None):
             pm, n_bt = predmode()
             lines.append(pm)
     return "\n".join(lines) + "\n"
+
+
+def random_f8_speeds(oracle, seed):
+    """four (inc, lim) pairs over the whole f8 range (up to 30720) for options(literal_adaptation=...): the encoder option that
+    overrides the PredictionMode speeds (context_map.rs:144-146)"""
+    rng = np.random.default_rng(seed)
+    L = oracle.lib()
+    return [(int(L.dvo_u8_to_speed(int(rng.integers(8, 128)))), int(L.dvo_u8_to_speed(int(rng.integers(8, 128))))) for _ in range(4)]

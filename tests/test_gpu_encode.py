@@ -93,6 +93,22 @@ def test_command_lists_random_ir(engine, oracle, text):
             _check(got[i], c.encode(oracle.options(**kw)), "random IR seed %d opts %s" % (i, kw))
 
 
+def test_reference_held_stream_is_reproduced_by_the_gpu_encoder(engine, oracle):
+    """Commands of the reference-held stream (wasm/wasm.html:98-107) -> GPU encoder under model revision WASM_2018 ->
+    the reference encoder's own 113 bytes; under today's revision -> the oracle's bytes for today's model."""
+    import divans_b200
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    vec = open(os.path.join(d, "ref_wasm_example.divans"), "rb").read()
+    rc, plain, cmds = oracle.decode_cmds(vec, model_rev=oracle.MODEL_WASM_2018)
+    assert rc == 0
+    blob = cmds.serialize()
+    kw = dict(window_size=22, use_context_map=0, dynamic_context_mixing=0)
+    got = engine.encode([blob, blob], divans_b200.encode_options(model_rev=divans_b200.MODEL_WASM_2018, **kw), cmds=True)
+    assert got[0] == vec and got[1] == vec
+    now = engine.encode([blob], divans_b200.encode_options(**kw), cmds=True)[0]
+    _check(now, cmds.encode(oracle.options(**kw)), "2018 commands under today's model")
+
+
 def test_bad_command_list_is_rejected_not_crashing(engine):
     blob = np.zeros(64, np.uint8)
     out = np.zeros(1 << 16, np.uint8)

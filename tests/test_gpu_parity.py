@@ -43,6 +43,29 @@ def test_golden_fixtures_one_warp_per_stream(engine32, oracle, golden):
         assert st == 0 and hashlib.sha256(out).hexdigest() == e["raw_sha256"], e["name"]
 
 
+def test_reference_held_stream(engine, engine32, oracle):
+    """The one compressed stream the reference tree holds (wasm/wasm.html:98-107, written by the reference's Rust encoder):
+    both lane layouts decode it bit-exactly under its model revision (include/divans_b200.h), CRC checked on the GPU; under
+    today's model revision it is rejected exactly like the oracle rejects it."""
+    import json
+    import divans_b200
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    vec = open(os.path.join(d, "ref_wasm_example.divans"), "rb").read()
+    meta = json.load(open(os.path.join(d, "ref_wasm_example.json")))
+    want = meta["plain_text"].encode("ascii")
+    assert want == b"It snowed, rained, and hailed the same morning.\n" * 7
+    for eng in (engine, engine32):
+        # a batch that mixes the 2018 stream with copies of itself exercises both groups of a warp
+        res = eng.decode([vec] * 5, [len(want) + 64] * 5, divans_b200.FLAG_MODEL_WASM_2018)
+        for st, out in res:
+            assert st == 0 and out == want
+        st, out = eng.decode([vec], [len(want) + 64])[0]
+        rc, ref = oracle.decode(vec, out_cap=len(want) + 64)
+        assert rc == oracle.NEEDS_MORE_INPUT and st == rc
+    rc, ref, _ = oracle.decode_cmds(vec, model_rev=oracle.MODEL_WASM_2018)
+    assert rc == 0 and ref == want
+
+
 def test_edge_lengths_literal_only(engine, oracle, text):
     raws = [text[:n] for n in [0, 1, 2, 7, 8, 9, 14, 15, 16, 17, 255, 4097, 32767, 32768, 32769, 70001]] + [bytes(range(256)) * 5]
     for win in [10, 22]:
@@ -102,6 +125,30 @@ def test_random_ir_fuzz_one_warp_per_stream(engine32, oracle, text):
         c = oracle.Commands.from_ir(irfuzz.random_ir(oracle, seed, n_cmds=100, window=16, text=text))
         streams.append(c.encode(oracle.options(window_size=16, dynamic_context_mixing=seed % 3)))
     _decode_and_compare(engine32, oracle, streams)
+
+
+def test_random_ir_fuzz_full_f8_speed_range(engine, engine32, oracle, text):
+    """Speeds are carried by the stream: the literal fast loops (32-bit adaptive arithmetic) must hand over to the generic
+    core (i16 wrap + the reference's literal LUT divide) whenever a counter could wrap.  GPU and oracle must agree on
+    status and on every output byte, whether or not the stream decodes back to its input."""
+    import irfuzz
+    streams = []
+    for seed in range(48):
+        win = [10, 14, 16, 22][seed % 4]
+        c = oracle.Commands.from_ir(irfuzz.random_ir(oracle, 7000 + seed, n_cmds=60, window=win, text=text, wide_speeds=True))
+        adapt = irfuzz.random_f8_speeds(oracle, seed) if seed % 2 else None
+        try:
+            streams.append(c.encode(oracle.options(window_size=win, dynamic_context_mixing=seed % 3, literal_adaptation=adapt)))
+        except ValueError:
+            pass   # a wrapped counter gave a coded symbol frequency <= 0: the reference encoder divides by it and panics
+    caps = [1 << 18] * len(streams)
+    for eng in (engine, engine32):
+        res = eng.decode(streams, caps, 1)   # FLAG_SKIP_CRC: payloads are well-formed, only the model misbehaves
+        for i, (st, out) in enumerate(res):
+            rc, ref = oracle.decode(streams[i], out_cap=caps[i], skip_crc=True)
+            assert st == rc, (i, st, rc)
+            if rc == 0:
+                assert out == ref, i
 
 
 def test_chunk_restart_every_65536_symbols(engine, oracle):
@@ -258,3 +305,71 @@ def test_pipelined_host_api_matches_blocking_call(engine, oracle, text):
     # and the out_len / status arrays of the last batch
     ol, st = results[-1]
     assert (st == 0).all() and (ol == batches[-1][6]).all()
+
+
+def test_host_api_writes_only_declared_regions_and_accepts_aliased_inputs(engine, oracle, text):
+    """(1) nothing outside out[out_off[i] .. +out_cap[i]) is written, by the blocking and by the pipelined call (guard bytes
+    between and around the regions survive); (2) input regions may alias: the same stream decoded n times."""
+    import torch
+    raws = [text[i * 5000: i * 5000 + 2000 + 700 * i] for i in range(12)]
+    streams = [oracle.encode_raw(r, oracle.options(window_size=16)) for r in raws]
+    in_len = np.array([len(s) for s in streams], np.uint64)
+    in_off = np.zeros(len(streams), np.uint64)
+    in_off[1:] = np.cumsum(in_len)[:-1]
+    blob = np.frombuffer(b"".join(streams), np.uint8).copy()
+    cap = np.array([len(r) + (0 if i % 3 else 40) for i, r in enumerate(raws)], np.uint64)    # some regions exactly full
+    gap = np.array([0 if i % 4 == 1 else 100 + 13 * i for i in range(len(raws))], np.uint64)  # some regions exactly adjacent
+    out_off = np.zeros(len(raws), np.uint64)
+    out_off[0] = 77
+    for i in range(1, len(raws)):
+        out_off[i] = out_off[i - 1] + cap[i - 1] + gap[i]
+    total = int(out_off[-1] + cap[-1]) + 333
+    covered = np.zeros(total, bool)
+    for o, c in zip(out_off, cap):
+        covered[int(o):int(o + c)] = True
+    for mode in ("blocking", "pipelined"):
+        out = torch.full((total,), 0xA5, dtype=torch.uint8).pin_memory().numpy()
+        if mode == "blocking":
+            ol, st = engine.decode_batch_host(blob, in_off, in_len, out, out_off, cap)
+        else:
+            ol, st = engine.decode_batch_host_async(blob, in_off, in_len, out, out_off, cap).wait()
+        assert (st == 0).all() and (ol == np.array([len(r) for r in raws], np.uint64)).all()
+        for r, o in zip(raws, out_off):
+            assert out[int(o):int(o) + len(r)].tobytes() == r
+        assert (out[~covered] == 0xA5).all(), mode
+    # aliased inputs: every descriptor points at the same bytes
+    n = 300
+    s0 = np.frombuffer(streams[5], np.uint8).copy()
+    caps = np.full(n, len(raws[5]), np.uint64)
+    offs = np.arange(n, dtype=np.uint64) * np.uint64(len(raws[5]))
+    out = np.zeros(n * len(raws[5]), np.uint8)
+    ol, st = engine.decode_batch_host(s0, np.zeros(n, np.uint64), np.full(n, s0.size, np.uint64), out, offs, caps)
+    assert (st == 0).all() and out.tobytes() == raws[5] * n
+
+
+def test_pipelined_call_survives_dropped_handles_and_empty_batches(oracle, text):
+    """A caller that drops the pending handle without wait(): the engine keeps the buffers alive and retires the batch itself
+    (next call on the lane, or close()).  An empty batch returns the no-op ticket."""
+    import gc
+    import divans_b200
+    eng = divans_b200.Engine(0, 64, 16)
+    raws = [text[i * 3000: i * 3000 + 4000] for i in range(8)]
+    streams = [oracle.encode_raw(r) for r in raws]
+    for rep in range(5):
+        h = eng.decode(streams, [len(r) for r in raws])          # warm
+        blob = np.frombuffer(b"".join(streams), np.uint8).copy()
+        in_len = np.array([len(s) for s in streams], np.uint64)
+        in_off = np.concatenate([[0], np.cumsum(in_len)[:-1]]).astype(np.uint64)
+        cap = np.array([len(r) for r in raws], np.uint64)
+        out_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64)
+        out = np.zeros(int(cap.sum()), np.uint8)
+        eng.decode_batch_host_async(blob, in_off, in_len, out, out_off, cap)   # handle dropped on the floor
+        del blob, out
+        gc.collect()
+    e = eng.decode_batch_host_async(np.zeros(1, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(1, np.uint8),
+                                    np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+    ol, st = e.wait()
+    assert len(ol) == 0 and len(st) == 0
+    res = eng.decode(streams, [len(r) for r in raws])
+    assert all(st == 0 and o == r for (st, o), r in zip(res, raws))
+    eng.close()
