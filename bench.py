@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("DIVANS_B200_LPS", "16")), help="lanes per stream: 32 or 16")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("DIVANS_B200_LPS", "8")), help="lanes per stream: 8 (default, 4 streams per warp), 16 or 32")
     ap.add_argument("--cpu-sample", type=int, default=0, help="streams in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -39,7 +39,7 @@ BATCH_SYMBOLS = [
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
     "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device", "divans_b200_ir_to_cmds",
-    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait",
+    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait", "divans_b200_lz77_cmds_batch",
 ]
 
 
@@ -105,6 +105,8 @@ def load_library():
     L.divans_b200_encode_batch_device.restype = ctypes.c_uint8
     L.divans_b200_ir_to_cmds.argtypes = [ctypes.c_char_p, sz, vp, sz, szp, ctypes.POINTER(ctypes.c_int32)]
     L.divans_b200_ir_to_cmds.restype = ctypes.c_uint8
+    L.divans_b200_lz77_cmds_batch.argtypes = [sz, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, sz, vp, vp, szp, ctypes.c_int32]
+    L.divans_b200_lz77_cmds_batch.restype = ctypes.c_uint8
     # reference FFI
     L.divans_new_decompressor.restype = vp
     L.divans_new_serial_decompressor.restype = vp
@@ -149,6 +151,28 @@ def ir_to_cmds(text):
     if rc != DIVANS_SUCCESS:
         raise ValueError("IR parse failed")
     return out.tobytes(), int(win.value)
+
+
+def lz77_cmds_batch(blob, in_off, in_len, window=16, pred_mode=2, mixing_value=4, n_threads=None):
+    """Raw buffers -> DVCL command lists by the library's greedy LZ77 (divans_b200_lz77_cmds_batch): returns
+    (blobs uint8 array, blob_off, blob_len) ready for Engine.encode_batch_host(..., cmds=True)."""
+    L = load_library()
+    blob = _u8(blob)
+    in_off, in_len = np.ascontiguousarray(in_off, np.uint64), np.ascontiguousarray(in_len, np.uint64)
+    n = len(in_off)
+    boff, blen = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    total = ctypes.c_size_t(0)
+    nt = int(n_threads or os.cpu_count() or 1)
+    rc = L.divans_b200_lz77_cmds_batch(n, _ptr(blob), _ptr(in_off), _ptr(in_len), window, pred_mode, mixing_value, None, 0, _ptr(boff), _ptr(blen),
+                                       ctypes.byref(total), nt)
+    if rc != DIVANS_NEEDS_MORE_OUTPUT and not (rc == DIVANS_SUCCESS and total.value == 0):
+        raise ValueError("lz77_cmds_batch failed")
+    out = np.zeros(max(1, total.value), np.uint8)
+    rc = L.divans_b200_lz77_cmds_batch(n, _ptr(blob), _ptr(in_off), _ptr(in_len), window, pred_mode, mixing_value, _ptr(out), out.size, _ptr(boff),
+                                       _ptr(blen), ctypes.byref(total), nt)
+    if rc != DIVANS_SUCCESS:
+        raise ValueError("lz77_cmds_batch failed")
+    return out, boff, blen
 
 
 def encode_options(**kw):

@@ -30,7 +30,8 @@ using namespace dv;
 
 struct divans_b200_ctx {
     int device = 0;
-    int lanes_per_stream = 32;
+    int lanes_per_stream = 8;
+    uint32_t groups_per_block = 4;   // decode: lane-groups (streams) per block of the selected layout
     int sm_count = 0;
     uint32_t max_resident = 0;       // slots in the arena
     cudaStream_t stream = nullptr;
@@ -94,7 +95,7 @@ static bool grow(divans_b200_ctx *ctx, T **p, size_t *cap, size_t need) {
 extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream) {
     divans_b200_ctx *ctx = new divans_b200_ctx();
     ctx->device = device;
-    ctx->lanes_per_stream = lanes_per_stream == 16 ? 16 : 32;
+    ctx->lanes_per_stream = lanes_per_stream == 16 ? 16 : (lanes_per_stream == 32 ? 32 : 8);   // default: the 8-lane engine
     cudaDeviceProp prop;
     if (!ck(ctx, cudaSetDevice(device), "cudaSetDevice") || !ck(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
         fprintf(stderr, "divans_b200: no usable CUDA device %d -- this library has no CPU path\n", device);
@@ -115,13 +116,14 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
               ck(ctx, cudaMalloc((void **)&ctx->d_nibbles, 64), "cudaMalloc(nibbles)") &&
               ck(ctx, cudaMemset(ctx->d_nibbles, 0, 64), "cudaMemset");
     if (!ok) { delete ctx; return nullptr; }
-    int per_sm = ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
+    int per_sm = ctx->lanes_per_stream == 8 ? decode_max_blocks_per_sm8() : ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
     if (per_sm < 1) per_sm = 1;
-    uint32_t groups_per_block = DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    uint32_t groups_per_block = ctx->lanes_per_stream == 8 ? (uint32_t)decode_groups_per_block8() : DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    ctx->groups_per_block = groups_per_block;
     uint32_t auto_res = (uint32_t)ctx->sm_count * (uint32_t)per_sm * groups_per_block;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    uint32_t mem_cap = (uint32_t)((free_b * 6 / 10) / SLOT_STRIDE);   // leave room for batch buffers
+    uint32_t mem_cap = (uint32_t)((free_b * 7 / 10) / SLOT_STRIDE);   // leave room for batch buffers
     if (auto_res > mem_cap) auto_res = mem_cap;
     ctx->max_resident = max_resident ? (max_resident < auto_res ? max_resident : auto_res) : auto_res;
     if (ctx->max_resident < groups_per_block) ctx->max_resident = groups_per_block;
@@ -179,6 +181,9 @@ static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
     if (slots <= ctx->arena_slots) return DIVANS_SUCCESS;
     if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; ctx->arena_slots = 0; }
     CK(cudaMalloc((void **)&ctx->d_arena, slots * SLOT_STRIDE));
+    // generation tags, context table and slot header must start out as zeros (tag 0 = never valid); everything else in a slot
+    // is initialised by the kernels
+    CK(cudaMemset2D(ctx->d_arena + OFF_TAGS_HI, SLOT_STRIDE, 0, PERSISTENT_BYTES, slots));
     ctx->arena_slots = slots;
     return DIVANS_SUCCESS;
 }
@@ -194,7 +199,7 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     if (ctx->busy_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
-    uint32_t gpb = DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    uint32_t gpb = ctx->groups_per_block;
     uint32_t resident = (uint32_t)(n < ctx->max_resident ? n : ctx->max_resident);
     uint32_t blocks = (resident + gpb - 1) / gpb;
     if (ensure_arena(ctx, (size_t)blocks * gpb) != DIVANS_SUCCESS) return DIVANS_FAILURE;
@@ -215,7 +220,7 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     launch_frame(fp, ctx->d_payload, (uint64_t)ctx->payload_cap, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
-    if (!skip_decode) { if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
+    if (!skip_decode) { if (ctx->lanes_per_stream == 8) launch_decode8(dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;

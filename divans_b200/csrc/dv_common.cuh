@@ -32,8 +32,22 @@ constexpr uint64_t MISC_CDFS = 128;
 constexpr uint64_t OFF_LCM = OFF_MISC + MISC_CDFS * CDF_BYTES;   // literal context map (== the recycled PredictionMode buffer)
 constexpr uint64_t OFF_MIX = OFF_LCM + 16384;                     // mixing mask
 constexpr uint64_t OFF_DCM = OFF_MIX + 8192;                      // distance context map
-constexpr uint64_t OFF_SLOT_END = OFF_DCM + 1024;
+// 8-lane engine (dv8_*.cu*): one generation tag byte per literal prior (a prior whose tag differs from the stream's
+// generation reads as the default CDF [4,8,...,64] and is tagged when it is first written: no per-stream initialisation of
+// the 12.6 MB of literal priors, not even of the reachable slabs), the per-stream context table
+// T2[byte][lut1 class] = literal_context_map[block type][lut0[byte] | class] (8 classes, codec/literal.rs:87-117 in one
+// lookup), and a small header that survives from launch to launch (generation counter).
+constexpr uint64_t OFF_TAGS_HI = OFF_DCM + 1024;
+constexpr uint64_t OFF_TAGS_LO = OFF_TAGS_HI + LIT_TABLE_CDFS;
+constexpr uint64_t OFF_T2 = OFF_TAGS_LO + LIT_TABLE_CDFS;
+constexpr uint64_t OFF_HDR = OFF_T2 + 2048;
+constexpr uint64_t OFF_SLOT_END = OFF_HDR + 64;
 constexpr uint64_t SLOT_STRIDE = ((OFF_SLOT_END + 4095) / 4096) * 4096;
+constexpr uint64_t PERSISTENT_BYTES = OFF_SLOT_END - OFF_TAGS_HI;   // zeroed once when the arena is allocated
+// low-nibble prior index of the 8-lane engine: [which][index_c >> 4][index_b][index_c & 15]
+__host__ __device__ __forceinline__ uint32_t lit_index_lo(uint32_t which, uint32_t index_c, uint32_t index_b) {
+    return (which << 16) | ((index_c >> 4) << 12) | (index_b << 4) | (index_c & 15u);
+}
 
 // CTYPE slab entries (indexed by the current command block type)
 constexpr int CT_LL_COUNT_SMALL = 0, CT_LL_SIZE_BEG = 1, CT_LL_SIZE_LAST = 2, CT_LL_MANTISSA = 3;

@@ -54,6 +54,7 @@ struct Next {
     int speed;         // inc | lim<<16 for `cdf`; SPK_NONE = read-only (mm_opts == 2: literal.rs:213-216,252-256)
     int sym;           // ENC: symbol to code
     bool mix_hi;       // mixing: which of the two weight sets / cm speeds (true = high nibble)
+    uint8_t *tag;      // 8-lane engine: generation tag of `cdf` (literal tables; nullptr = the prior is always initialised)
 };
 // A blend with inc 0 and an unreachable limit leaves the CDF bit-identical: "do not adapt" without a branch.
 #define SPK_NONE sp_pack(0, 0x7fff)
@@ -92,6 +93,8 @@ struct Cold {
     uint32_t lit_log_cap;                    // encoder: capacity (entries) of the literal coder's log
     uint32_t sidx;                           // stream index being processed
     uint32_t model_rev;                      // DecodeParams::model_rev
+    uint32_t gen_ctr;                        // 8-lane engine: streams this slot has hosted (generation of the literal-prior tags)
+    bool t2_dirty;                           // 8-lane engine: the slot's context table (OFF_T2) does not match lcm / mode / block type
     // encoder
     CmdIn in;
     uint32_t e0, e1, e2, e3;                 // current input command fields
@@ -120,6 +123,7 @@ struct St {
     int status;
     uint32_t f0, f1, f2, f3;                 // scratch of the command being coded (meaning depends on the state)
     uint32_t lit_left, lit_ctx, lit_h;       // literal in flight
+    uint32_t gen;                            // 8-lane engine: tag value of literal priors that belong to the current stream (1..255)
 };
 
 // arena accessors
@@ -132,11 +136,12 @@ __device__ __forceinline__ uint8_t *A_dcm(const St &s) { return s.slot + OFF_DCM
 __device__ __forceinline__ uint32_t BL(const St &s, int k, int j) { return (uint32_t)(s.c->btype_lru >> (8 * (2 * k + j))) & 0xffu; }
 __device__ __forceinline__ uint32_t BMAX(const St &s, int k) { return (s.c->btype_max >> (8 * k)) & 0xffu; }
 
-struct G2 {            // lane geometry
-    int l16;           // lane & 15
-    int shift;         // 0 / 16
+struct G2 {            // lane geometry of one lane-group (16 lanes: one CDF element per lane; 8 lanes: two per lane)
+    int l16;           // lane index inside the group: lane & 15 (16/32 lanes per stream) or lane & 7 (8 lanes per stream)
+    int shift;         // position of the group's ballot bits: 0 / 16, or 0 / 8 / 16 / 24
     unsigned gmask;    // this group's lanes
     bool store0;       // lane that performs the group's scalar stores
+    int nl;            // lanes that share the group's loops: 16 or 8
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -147,7 +152,7 @@ __device__ __forceinline__ void store_default_cdfs(const G2 g, int16_t *base, ui
     const uint4 hi = make_uint4(0x00280024u, 0x0030002cu, 0x00380034u, 0x0040003cu);
     uint4 *p = reinterpret_cast<uint4 *>(base);
     uint32_t n16 = n_cdfs * 2;
-    for (uint32_t i = g.l16; i < n16; i += 16) p[i] = (i & 1) ? hi : lo;
+    for (uint32_t i = g.l16; i < n16; i += g.nl) p[i] = (i & 1) ? hi : lo;
 }
 static __device__ __noinline__ void init_slab32(const G2 g, int16_t *p, uint32_t *bm, uint32_t idx) {
     store_default_cdfs(g, p, 32);
@@ -226,12 +231,35 @@ static __device__ __noinline__ int ensure_literal_slabs(const G2 g, uint8_t *slo
     return (present & (present - 1)) == 0 ? (__ffs(present) - 1) : -1;
 }
 
+// 8-lane engine: what ensure_literal_slabs finds out without initialising anything (the literal priors are tagged):
+// the uniform mixing value (or -1); the context-map priors of dynamic context mixing >= 2 are still defaulted eagerly, once.
+static __device__ __noinline__ int scan_literal_config(const G2 g, uint8_t *slot, uint32_t *bitmaps, bool mixing_trait) {
+    uint32_t present = 0;
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(slot + OFF_MIX);
+    for (uint32_t i = 0; i < 512; i++) {
+        uint4 v = x4[i];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            present |= 1u << (w[j] & 15); present |= 1u << ((w[j] >> 8) & 15);
+            present |= 1u << ((w[j] >> 16) & 15); present |= 1u << ((w[j] >> 24) & 15);
+        }
+    }
+    if (mixing_trait && !(bitmaps[64] & 1u)) {   // lit_cm_priors are allocated on the first mixing>=2 (codec/interface.rs:322-329)
+        store_default_cdfs(g, reinterpret_cast<int16_t *>(slot + OFF_LIT_CM), (uint32_t)LIT_CM_CDFS);
+        __syncwarp(g.gmask);
+        if (g.store0) bitmaps[64] |= 1u;
+    }
+    __syncwarp(g.gmask);
+    return (present & (present - 1)) == 0 ? (__ffs(present) - 1) : -1;
+}
+
 // fresh arena state for a new stream: zero the maps (ffi/alloc_util.rs:70-99), clear slab bitmaps, default the dense priors
 static __device__ __noinline__ void reset_slot(const G2 g, uint8_t *slot, uint32_t *bitmaps) {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_LCM);
-    for (uint32_t i = g.l16; i < (16384 + 8192 + 1024) / 16; i += 16) p[i] = z;   // lcm, mix, dcm are contiguous
-    for (uint32_t i = g.l16; i < 65; i += 16) bitmaps[i] = 0;
+    for (uint32_t i = g.l16; i < (16384 + 8192 + 1024) / 16; i += g.nl) p[i] = z;   // lcm, mix, dcm are contiguous
+    for (uint32_t i = g.l16; i < 65; i += g.nl) bitmaps[i] = 0;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(slot + OFF_MISC), (uint32_t)MISC_CDFS);
     __syncwarp(g.gmask);
 }
@@ -242,8 +270,8 @@ static __device__ __noinline__ void replay_copy(const G2 g, uint8_t *out, uint32
     long long base = (long long)pos - (long long)dist;
     uint8_t *dst = out + pos;
     uint32_t off = (uint32_t)g.l16 % dist;
-    uint32_t step = 16u % dist;
-    for (uint32_t i = (uint32_t)g.l16; i < len; i += 16) {
+    uint32_t step = (uint32_t)g.nl % dist;
+    for (uint32_t i = (uint32_t)g.l16; i < len; i += g.nl) {
         long long sp = base + (long long)off;
         dst[i] = sp >= 0 ? out[sp] : (uint8_t)0;   // a fresh ring is zero-initialised (ffi/alloc_util.rs:70-99)
         off += step; if (off >= dist) off -= dist;

@@ -29,7 +29,7 @@ __device__ __forceinline__ int load_cmd(St &s) {
 template <bool ENC>
 __device__ __forceinline__ void enter_cmd_type(St &s, Next &nx) {
     s.state = S_CMD_TYPE;
-    nx.cdf = A_misc(s, MI_CC + (int)(s.c->last_4_states >> 4)); nx.cdf2 = nullptr; nx.speed = SPK_ROCKET;
+    nx.cdf = A_misc(s, MI_CC + (int)(s.c->last_4_states >> 4)); nx.cdf2 = nullptr; nx.speed = SPK_ROCKET; nx.tag = nullptr;
     if (ENC) {
         if (s.c->in.pos < s.c->in.n_cmds) nx.sym = load_cmd<ENC>(s);
         else nx.sym = 0xf;   // end of stream nibble (codec/mod.rs:143-148, flush :424-455)
@@ -48,7 +48,7 @@ __device__ __forceinline__ int mm_cfg(uint32_t mm_opts) {
     return (int)(which | ((0x38u - stride_offset) << 2) | (mm << 8) | (o1 << 9) | (fc << 10) | (ro << 11));
 }
 // literal nibble prior selection (codec/literal.rs:154-259)
-template <bool ENC, bool HIGH>
+template <bool ENC, bool HIGH, bool V2 = false>
 __device__ __forceinline__ void enter_lit_nibble(St &s, Next &nx) {
     const uint32_t ctx = s.lit_ctx;
     int cfg = s.lit_cfg;
@@ -62,9 +62,14 @@ __device__ __forceinline__ void enter_lit_nibble(St &s, Next &nx) {
     if (HIGH) { index_b = ssb & mm & (~o1 & 0xffu); index_c = ctx; }
     else { index_b = (mm & ssb) | ((~mm & 0xffu) & ctx); index_c = (s.lit_h & fc) | ((ctx & o1) << 4); }
     const uint32_t which = (uint32_t)cfg & 3u;
-    int16_t *np = A_lit(s, HIGH) + ((size_t)((which * 256 + index_c) * 256 + index_b)) * 16;
+    // 8-lane engine: the low-nibble table is laid out [index_c >> 4][index_b][index_c & 15] so that the 16 candidates of the
+    // next low nibble (one per value of the high nibble) are 512 contiguous bytes (lit_index_lo, dv_common.cuh)
+    const uint32_t flat = (V2 && !HIGH) ? lit_index_lo(which, index_c, index_b) : (which * 256 + index_c) * 256 + index_b;
+    int16_t *np = A_lit(s, HIGH) + (size_t)flat * 16;
     const bool ro = (cfg & 0x800) != 0;
     nx.mix_hi = HIGH;
+    // (the never-adapted flat prior of mixing value 2 has no tag; with dynamic context mixing the stride prior is still READ)
+    nx.tag = (V2 && (s.mixing_trait || !ro)) ? s.slot + (HIGH ? OFF_TAGS_HI : OFF_TAGS_LO) + flat : nullptr;
     if (s.mixing_trait) {
         nx.cdf = np; nx.speed = ro ? SPK_NONE : s.ad_stride;
         nx.cdf2 = HIGH ? A_litcm(s) + (size_t)ctx * 16 : A_litcm(s) + (size_t)(256 + s.lit_h + 16 * ctx) * 16;
@@ -103,10 +108,14 @@ __device__ __forceinline__ unsigned long long reseed_last8(const St &s) {
 }
 __device__ __forceinline__ void swap_coders(St &s) { Coder t = s.cur; s.cur = s.c->oth; s.c->oth = t; s.c->cur_is_lit = !s.c->cur_is_lit; }
 
-template <bool ENC>
+template <bool ENC, bool V2 = false>
 __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint32_t len) {
     if ((uint64_t)len > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
-    if (!s.c->lit_slabs_ready) { int u = ensure_literal_slabs(g, s.slot, s.c->bitmaps, s.mixing_trait); s.lit_cfg = u >= 0 ? mm_cfg((uint32_t)u) : -1; s.c->lit_slabs_ready = true; }
+    if (!s.c->lit_slabs_ready) {
+        // 8-lane engine: literal priors carry generation tags and are defaulted on first touch -- nothing to initialise
+        int u = V2 ? scan_literal_config(g, s.slot, s.c->bitmaps, s.mixing_trait) : ensure_literal_slabs(g, s.slot, s.c->bitmaps, s.mixing_trait);
+        s.lit_cfg = u >= 0 ? mm_cfg((uint32_t)u) : -1; s.c->lit_slabs_ready = true;
+    }
     s.l8 = reseed_last8(s);
     swap_coders(s);
     s.lit_left = len;
@@ -116,7 +125,7 @@ __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint3
         if ((uint64_t)s.c->e0 + len > s.c->raw_len || (uint64_t)s.cur.left + 2ull * len > s.c->lit_log_cap) { s.status = ST_FAIL; return; }
     }
     lit_context(s);
-    enter_lit_nibble<ENC, true>(s, nx);
+    enter_lit_nibble<ENC, true, V2>(s, nx);
 }
 
 __device__ __forceinline__ void obs_distance(St &s, uint32_t d) {   // codec/interface.rs:509-527
@@ -140,7 +149,7 @@ __device__ __forceinline__ void obs_btype(St &s, int k, uint32_t bt) {   // code
 }
 
 template <bool ENC> __device__ __forceinline__ void set_next(Next &nx, int16_t *cdf, int speed, int sym) {
-    nx.cdf = cdf; nx.cdf2 = nullptr; nx.speed = speed;
+    nx.cdf = cdf; nx.cdf2 = nullptr; nx.speed = speed; nx.tag = nullptr;
     if (ENC) nx.sym = sym;
 }
 
@@ -262,10 +271,10 @@ template <bool ENC> __device__ __forceinline__ void pm_map_store(St &s, Next &nx
 }
 
 // The transition: consume the nibble just coded in state s.state, perform its side effects, choose the next prior.
-template <bool ENC>
+template <bool ENC, bool V2 = false>
 __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib) {
     // ---- hot: literal nibbles ----
-    if (s.state == S_LIT_HI) { s.lit_h = (uint32_t)nib; enter_lit_nibble<ENC, false>(s, nx); return; }
+    if (s.state == S_LIT_HI) { s.lit_h = (uint32_t)nib; enter_lit_nibble<ENC, false, V2>(s, nx); return; }
     if (s.state == S_LIT_LO) {
         uint32_t cur = ((uint32_t)nib | (s.lit_h << 4)) & 0xff;
         s.l8 = (s.l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
@@ -275,7 +284,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             swap_coders(s);
             if (ENC) s.c->in.pos++;
             enter_cmd_type<ENC>(s, nx);
-        } else { lit_context(s); enter_lit_nibble<ENC, true>(s, nx); }
+        } else { lit_context(s); enter_lit_nibble<ENC, true, V2>(s, nx); }
         return;
     }
     switch (s.state) {
@@ -291,7 +300,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         else if (nib == 6) enter_bt_mnemonic<ENC>(s, nx, 2);
         else if (nib == 7) {
             cmap_reset(s);                                                        // reset_context_map_lru
-            for (uint32_t i = g.l16; i < 1024; i += 16) A_dcm(s)[i] = (uint8_t)(i & 3);   // reset_distance_context_map
+            for (uint32_t i = g.l16; i < 1024; i += g.nl) A_dcm(s)[i] = (uint8_t)(i & 3);   // reset_distance_context_map
             if (ENC) {   // encoder speed wishes, context_map.rs:123-146
                 int d[4] = {SPK_MUD, SPK_MUD, SPK_MUD, SPK_MUD};
                 const uint8_t *r = pm_rec<ENC>(s);
@@ -318,20 +327,20 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             uint32_t lllen = bitlen32(s.c->e1 - 15u);
             set_next<ENC>(nx, ctype_slab(s, g, BL(s, 1, 0)) + CT_LL_SIZE_BEG * 16, SPK_MUD, (int)(lllen < 15 ? lllen : 15));
         } else if (nib == 15) { s.f3 = 1; enter_ll_count_small<ENC>(s, nx, g); }
-        else { uint32_t len = (uint32_t)nib + 1; s.c->last_llen = len; start_literal<ENC>(s, nx, g, len); }
+        else { uint32_t len = (uint32_t)nib + 1; s.c->last_llen = len; start_literal<ENC, V2>(s, nx, g, len); }
     } break;
     case S_LL_SIZE_BEG: {
         if (nib == 15) {
             s.state = S_LL_SIZE_LAST;
             set_next<ENC>(nx, ctype_slab(s, g, BL(s, 1, 0)) + CT_LL_SIZE_LAST * 16, SPK_MUD, (int)((bitlen32(s.c->e1 - 15u) - 15u) & 0xf));
-        } else if (nib <= 1) start_literal<ENC>(s, nx, g, 15u + (uint32_t)nib);   // last_llen NOT updated (literal.rs:608-616)
+        } else if (nib <= 1) start_literal<ENC, V2>(s, nx, g, 15u + (uint32_t)nib);   // last_llen NOT updated (literal.rs:608-616)
         else { s.f0 = round_up_mod_4((uint32_t)nib - 1); s.f1 = 1u << (nib - 1); enter_ll_mant<ENC>(s, nx, g); }
     } break;
     case S_LL_SIZE_LAST: { s.f0 = round_up_mod_4((uint32_t)nib + 14); s.f1 = 1u << (nib + 14); enter_ll_mant<ENC>(s, nx, g); } break;
     case S_LL_MANT: {
         uint32_t next_rem = s.f0 - 4;
         s.f1 |= (uint32_t)nib << next_rem;
-        if (next_rem == 0) { uint32_t len = s.f1 + 15u; s.c->last_llen = len; start_literal<ENC>(s, nx, g, len); }
+        if (next_rem == 0) { uint32_t len = s.f1 + 15u; s.c->last_llen = len; start_literal<ENC, V2>(s, nx, g, len); }
         else { s.f0 = next_rem; enter_ll_mant<ENC>(s, nx, g); }
     } break;
     // ---- copy ----
@@ -419,7 +428,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         if (n < 0) { s.status = ST_FAIL; return; }
         __syncwarp(g.gmask);
         if ((uint64_t)n > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
-        for (int i = g.l16; i < n; i += 16) s.out[s.out_pos + i] = scratch[i];
+        for (int i = g.l16; i < n; i += g.nl) s.out[s.out_pos + i] = scratch[i];
         __syncwarp(g.gmask);
         s.out_pos += (uint32_t)n;
         if (ENC) s.c->in.pos++;
@@ -435,7 +444,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
     } break;
     case S_BT_FIRST: { s.f1 = (uint32_t)nib; s.state = S_BT_SECOND; set_next<ENC>(nx, A_misc(s, MI_BTYPE + BT_SECOND + (int)s.f0), SPK_SLOW, (int)((s.c->e0 >> 4) & 0xf)); } break;
     case S_BT_SECOND: bt_done<ENC>(s, nx, ((uint32_t)nib << 4) | s.f1); break;
-    case S_BT_STRIDE: { obs_btype(s, 0, s.f1); s.btype_last = s.f1; if (ENC) s.c->in.pos++; enter_cmd_type<ENC>(s, nx); } break;
+    case S_BT_STRIDE: { obs_btype(s, 0, s.f1); s.btype_last = s.f1; s.c->t2_dirty = true; if (ENC) s.c->in.pos++; enter_cmd_type<ENC>(s, nx); } break;
     // ---- prediction mode ----
     case S_PM_MODE: {
         s.f0 = (uint32_t)nib; s.state = S_PM_MIX;
@@ -485,7 +494,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             s.c->ad_cm_lo = f8_pair_to_speed((uint32_t)(a >> 32) & 0xff, (uint32_t)(a >> 40) & 0xff);
             s.c->ad_cm_hi = f8_pair_to_speed((uint32_t)(a >> 48) & 0xff, (uint32_t)(a >> 56) & 0xff);
             s.speeds_small = speed_is_small(s.ad_stride) && speed_is_small(s.c->ad_cm_lo) && speed_is_small(s.c->ad_cm_hi);
-            s.c->lit_slabs_ready = false;
+            s.c->lit_slabs_ready = false; s.c->t2_dirty = true;
             if (ENC) s.c->in.pos++;
             enter_cmd_type<ENC>(s, nx);
         } else enter_pm_mixval<ENC>(s, nx);
@@ -508,7 +517,7 @@ __device__ __forceinline__ void st_reset(St &s) {
     s.c->w_lo.w0 = s.c->w_lo.w1 = 1; s.c->w_lo.norm = 1 << 14; s.c->w_hi = s.c->w_lo;
     s.speeds_small = true;   // MUD
     s.c->mixing_param = 1; s.mixing_trait = false; s.c->lit_slabs_ready = false; s.lit_cfg = -1;
-    s.status = ST_OK; s.c->cur_is_lit = false;
+    s.status = ST_OK; s.c->cur_is_lit = false; s.c->t2_dirty = true;
     s.f0 = s.f1 = s.f2 = s.f3 = 0; s.lit_left = s.lit_ctx = s.lit_h = 0;
     s.c->e0 = s.c->e1 = s.c->e2 = s.c->e3 = 0;
 }

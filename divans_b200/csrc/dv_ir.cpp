@@ -181,3 +181,80 @@ extern "C" DivansResult divans_b200_ir_to_cmds(const char *ir_text, size_t ir_le
     if (!ps.lits.empty()) memcpy(w, ps.lits.data(), ps.lits.size());
     return DIVANS_SUCCESS;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Command generator for benchmarks and tools (ours, not a reference component): a deterministic greedy hash-chain LZ77
+// (minimum match 4, window 2^window - 16, no dictionary words) that turns raw bytes into a DVCL command list -- one
+// PredictionMode command (64-entry identity context map, one mixing value, like raw_to_cmd/mod.rs:116-143), then Literal /
+// Copy commands.  SURVEY 8d calls the resulting population "Z": copy-dominated streams like the reference's default
+// (brotli-driven) compressor produces.  The command SELECTION of the brotli crate stays out of scope.
+// ---------------------------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <thread>
+
+namespace {
+size_t lz77_blob(const uint8_t *in, size_t n, int window, int pred_mode, int mixing_value, std::vector<uint8_t> &blob) {
+    std::vector<Cmd> cmds;
+    cmds.push_back({7, 0, 0, 0, 0});
+    const int HB = 15;
+    std::vector<int32_t> head((size_t)1 << HB, -1), prev(n + 1, -1);
+    const size_t maxdist = ((size_t)1 << window) - 16;
+    auto h4 = [&](size_t i) {
+        uint32_t v; memcpy(&v, in + i, 4);
+        return (v * 2654435761u) >> (32 - HB);
+    };
+    size_t i = 0, lit_start = 0;
+    auto insert = [&](size_t at) { if (at + 4 <= n) { const uint32_t hh = h4(at); prev[at] = head[hh]; head[hh] = (int32_t)at; } };
+    while (i < n) {
+        size_t best_len = 0, best_dist = 0;
+        if (i + 4 <= n) {
+            int chain = 16;
+            for (int32_t c = head[h4(i)]; c >= 0 && chain-- > 0 && i - (size_t)c <= maxdist; c = prev[c]) {
+                size_t l = 0, lim = std::min<size_t>(n - i, 65535);
+                while (l < lim && in[c + l] == in[i + l]) l++;
+                if (l > best_len) { best_len = l; best_dist = i - (size_t)c; }
+            }
+        }
+        if (best_len >= 4) {
+            if (i > lit_start) cmds.push_back({3, (uint32_t)lit_start, (uint32_t)(i - lit_start), 0, 0});
+            cmds.push_back({1, (uint32_t)best_dist, (uint32_t)best_len, 0, 0});
+            for (size_t k = 0; k < best_len; k++) insert(i++);
+            lit_start = i;
+        } else insert(i++);
+    }
+    if (n > lit_start) cmds.push_back({3, (uint32_t)lit_start, (uint32_t)(n - lit_start), 0, 0});
+    constexpr size_t PM_BYTES = 32 + 16384 + 1024 + 8192;
+    blob.assign(32 + cmds.size() * 20 + PM_BYTES + n, 0);
+    uint8_t *w = blob.data();
+    const uint32_t hdr[8] = {0x4c435644u, 1u, (uint32_t)cmds.size(), 1u, (uint32_t)n, (uint32_t)window, 0u, 0u};
+    memcpy(w, hdr, 32); w += 32;
+    memcpy(w, cmds.data(), cmds.size() * 20); w += cmds.size() * 20;
+    w[0] = (uint8_t)pred_mode; w[2] = 1; w[28] = 64; w[30] = 4;
+    for (int k = 0; k < 64; k++) w[32 + k] = (uint8_t)k;
+    for (int k = 0; k < 4; k++) w[32 + 16384 + k] = (uint8_t)k;
+    memset(w + 32 + 16384 + 1024, mixing_value, 8192);
+    w += PM_BYTES;
+    if (n) memcpy(w, in, n);   // the literal pool is the raw stream itself: a Literal's offset is its position
+    return blob.size();
+}
+}  // namespace
+
+// n raw buffers -> n DVCL blobs written back to back at blob_off[i] (16-byte aligned) of `out`; blob_len[i] receives the sizes.
+// With out == NULL or out_cap too small the call returns DIVANS_NEEDS_MORE_OUTPUT and *total receives the size needed.
+extern "C" DivansResult divans_b200_lz77_cmds_batch(size_t n, const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len, int32_t window,
+                                                    int32_t pred_mode, int32_t mixing_value, uint8_t *out, size_t out_cap, uint64_t *blob_off,
+                                                    uint64_t *blob_len, size_t *total, int32_t n_threads) {
+    if (!in || !in_off || !in_len || !blob_off || !blob_len || !total || window < 10 || window > 24) return DIVANS_FAILURE;
+    std::vector<std::vector<uint8_t>> blobs(n);
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&, t]() { for (size_t i = (size_t)t; i < n; i += (size_t)n_threads) lz77_blob(in + in_off[i], (size_t)in_len[i], window, pred_mode, mixing_value, blobs[i]); });
+    for (auto &x : th) x.join();
+    size_t pos = 0;
+    for (size_t i = 0; i < n; i++) { blob_off[i] = pos; blob_len[i] = blobs[i].size(); pos += (blobs[i].size() + 15) & ~(size_t)15; }
+    *total = pos;
+    if (!out || out_cap < pos) return DIVANS_NEEDS_MORE_OUTPUT;
+    for (size_t i = 0; i < n; i++) memcpy(out + blob_off[i], blobs[i].data(), blobs[i].size());
+    return DIVANS_SUCCESS;
+}

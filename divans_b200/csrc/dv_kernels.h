@@ -9,6 +9,9 @@ void launch_frame(const FrameParams &p, uint8_t *payload, uint64_t payload_cap_b
 void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 int decode_max_blocks_per_sm32();
+void launch_decode8(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);   // 8-lane engine: 4 streams per warp (dv8_kernels.cu)
+int decode_max_blocks_per_sm8();
+int decode_groups_per_block8();
 int decode_max_blocks_per_sm16();
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st);                  // reverse rANS + mux/CRC (2 launches)

@@ -114,7 +114,8 @@ typedef struct divans_b200_ctx divans_b200_ctx;
 /* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
 
 /* device = CUDA ordinal; max_resident = cap on concurrently resident streams (0 = auto: sized to the GPU);
- * lanes_per_stream = 32 (one warp owns one stream) or 16 (two streams share a warp); 0 = default (32). */
+ * lanes_per_stream = 8 (default, also for 0: four streams per warp, two CDF elements per lane -- the fast engine), 16 (two
+ * streams per warp, one element per lane) or 32 (one warp owns one stream, the upper half-warp mirrors the lower). */
 divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream);
 void divans_b200_destroy(divans_b200_ctx *ctx);
 const char *divans_b200_last_error(divans_b200_ctx *ctx);
@@ -198,6 +199,14 @@ DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, 
  * DIVANS_NEEDS_MORE_OUTPUT.  *window_size (optional) receives the `window` line's value (0 if absent).  Host only. */
 DivansResult divans_b200_ir_to_cmds(const char *ir_text, size_t ir_len, uint8_t *out, size_t out_cap, size_t *blob_len,
                                     int32_t *window_size);
+/* Command generator for benchmarks / tools (ours, not a reference component): deterministic greedy hash-chain LZ77 (min
+ * match 4, no dictionary words) -> one DVCL blob per raw buffer: a PredictionMode command (64-entry identity context map,
+ * `mixing_value` everywhere, like src/raw_to_cmd/mod.rs:116-143) followed by Literal / Copy commands.  Blobs are written
+ * at blob_off[i] (16-byte aligned) of `out`; with out == NULL or out_cap too small the call returns
+ * DIVANS_NEEDS_MORE_OUTPUT and *total receives the size needed.  Host only, n_threads worker threads. */
+DivansResult divans_b200_lz77_cmds_batch(size_t n, const uint8_t *in, const uint64_t *in_off, const uint64_t *in_len, int32_t window,
+                                         int32_t pred_mode, int32_t mixing_value, uint8_t *out, size_t out_cap, uint64_t *blob_off,
+                                         uint64_t *blob_len, size_t *total, int32_t n_threads);
 /*
  * command list blob ("DVCL", little endian) -- the binary form of the reference's IR (src/bin/divans.rs:191-483):
  *   u32 magic 0x4c435644, u32 version 1, u32 n_cmds, u32 n_predmodes, u32 n_literal_bytes, u32 window, u32[2] 0

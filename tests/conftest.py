@@ -32,7 +32,15 @@ def golden():
 @pytest.fixture(scope="session")
 def engine():
     import divans_b200
-    eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "16")))
+    eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "8")))   # default: the 8-lane engine (4 streams per warp)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def engine16():
+    import divans_b200
+    eng = divans_b200.Engine(0, 64, 16)
     yield eng
     eng.close()
 

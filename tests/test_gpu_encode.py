@@ -96,6 +96,7 @@ def test_command_lists_random_ir(engine, oracle, text):
 def test_reference_held_stream_is_reproduced_by_the_gpu_encoder(engine, oracle):
     """Commands of the reference-held stream (wasm/wasm.html:98-107) -> GPU encoder under model revision WASM_2018 ->
     the reference encoder's own 113 bytes; under today's revision -> the oracle's bytes for today's model."""
+    import os
     import divans_b200
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     vec = open(os.path.join(d, "ref_wasm_example.divans"), "rb").read()

@@ -17,7 +17,8 @@ def run(name, raws, opts, eng, cmds=None):
     print("%-34s n=%5d raw %7.1f MB ratio %.3f | decode %8.2f ms (main %8.2f) %7.0f MB/s | encode %8.2f ms (model %8.2f) %7.0f MB/s | ok=%s"
           % (name, len(raws), tot / 1e6, comp / tot, dec_ms, dec_main, tot / dec_ms / 1e3, enc_ms, enc_model, tot / enc_ms / 1e3, ok), flush=True)
 
-eng = divans_b200.Engine(0, 0, 16)
+import os
+eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "8")))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 blob, off, ln = synth.text_streams(n, 65536, seed=3)
 raws = [blob[int(o):int(o + l)].tobytes() for o, l in zip(off, ln)]
