@@ -5,12 +5,17 @@
   python bench.py --impl reference [...]                         the reference arm: the CPU decoder on the host cores
 
 A "step" = one pass of the hot path over one batch: every rank decodes its shard of independent streams
-(configs[1]: 4096 x 64 KiB synthetic-text streams per GPU; weak scaling: the per-GPU batch is fixed as N grows).
+(N = 1: BASELINE configs[1], 4096 x 64 KiB synthetic-text streams; N > 1: configs[2], 8192 streams per GPU -- weak scaling: the
+per-GPU batch is fixed as N grows).
 `value` times K steps with inputs resident in HBM (CUDA events on the launching stream, max over ranks);
 `e2e` repeats the measurement through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed
 region).  `roofline` is computed for the stream-decode kernel from its own CUDA-event time; `cpu_baseline` times the
 CPU oracle (restatement of the reference algorithm; the Rust reference cannot be built in this image) on a bounded
-sample of the same streams.
+sample of the same streams.  `populations` repeats the device-resident measurement for the other encodings of the same raw
+streams (L = literal-only, the headline; Z = LZ77 command streams; dynamic context mixing 2; UTF8 context mode), each
+checked bit-exact against the raw input.  With N > 1, `scattered_e2e` times the sharded API (divans_b200.sharding.ShardedDecoder):
+rank 0 owns the whole host batch, scatters it over NVLink, every rank decodes, rank 0 gathers.
+  python bench.py --workload entropy       BASELINE configs[4]: 128 x 1 MiB Bernoulli streams per GPU, p in {0.5, 0.9, 0.99}
 """
 import argparse
 import json
@@ -26,7 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 STREAM_BYTES = 65536
-STREAMS_PER_GPU = 4096
+STREAMS_PER_GPU = 4096           # N = 1 (BASELINE configs[1])
+STREAMS_PER_GPU_SCALING = 8192   # N > 1 (BASELINE configs[2]: 65536 streams at 8 GPUs)
 METRIC = "decompressed MB/s (batched 64KiB streams)"
 UNIT = "MB/s"
 
@@ -137,48 +143,184 @@ def encode_inputs(blob, off, ln, engine):
     return comp, coff, out_len.astype(np.uint64), gen
 
 
+def _pin_all_cores():
+    """the CPU arm uses every core the process may run on, and says so"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _oracle_times(O, comp, coff, clen, off, ln, threads, reps):
+    """seconds per pass (median of `reps`) of the oracle's threaded batch decoder over the given streams, after one warm pass
+    (the per-thread prior tables are touched once: first-touch page placement is not what the arm measures)"""
+    O.decode_batch(comp, coff, clen, off, ln, threads)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out, out_len, status = O.decode_batch(comp, coff, clen, off, ln, threads)
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), out, status
+
+
 def cpu_baseline(comp, coff, clen, raw_blob, off, ln, n_sample, threads):
     from oracle import oracle_py as O
     n = min(n_sample, len(coff))
-    t0 = time.perf_counter()
-    out, out_len, status = O.decode_batch(comp, coff[:n], clen[:n], off[:n], ln[:n], threads)
-    dt = time.perf_counter() - t0
+    dt, out, status = _oracle_times(O, comp, coff[:n], clen[:n], off[:n], ln[:n], threads, 3)
+    n1 = min(n, 48)
+    dt1, _, _ = _oracle_times(O, comp, coff[:n1], clen[:n1], off[:n1], ln[:n1], 1, 1)
     ok = bool((status == 0).all() and (out[: n * STREAM_BYTES] == raw_blob[: n * STREAM_BYTES]).all())
     return {"value": n * STREAM_BYTES / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d of the benchmark's 64 KiB streams, oracle decode_batch, %.2f s" % (n, dt), "bit_exact_vs_input": ok}, out
+            "sample": "%d of the benchmark's 64 KiB streams, oracle decode_batch, median of 3 passes of %.2f s after a warm pass" % (n, dt),
+            "single_thread_value": n1 * STREAM_BYTES / dt1 / 1e6, "bit_exact_vs_input": ok}, out
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port: the Rust crate cannot be
-    compiled in this image) on all host threads, same workload/metric; bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the Rust crate cannot be compiled in
+    this image) on all host threads, same workload / metric.  Every step decodes the same fixed sample (2048 streams) after one
+    untimed warm pass per thread pool; the line reports the MEDIAN step (a CPU arm on a shared host moves a lot between
+    boxes: the median of >= 5 steps and the fixed sample are what keep it comparable) and the single-thread figure."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle_py as O
     O.build()
-    threads = os.cpu_count() or 1
-    n_sample = int(os.environ.get("DIVANS_BENCH_REF_STREAMS", str(max(64, 16 * threads))))
+    threads = _pin_all_cores()
+    n_sample = int(os.environ.get("DIVANS_BENCH_REF_STREAMS", "2048"))
     blob, off, ln = make_inputs(0, n_sample)
     enc, eoff, elen = O.encode_batch(blob, off, ln, O.options(), threads)
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):
         O.decode_batch(enc, eoff, elen, off, ln, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    steps = max(5, args.steps)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
         out, out_len, status = O.decode_batch(enc, eoff, elen, off, ln, threads)
-    dt = time.perf_counter() - t0
+        ts.append(time.perf_counter() - t0)
     assert (status == 0).all() and (out[: blob.size] == blob).all()
-    v = args.steps * blob.size / dt / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
+    dt = float(np.median(ts))
+    n1 = min(n_sample, 48)
+    dt1, _, _ = _oracle_times(O, enc, eoff[:n1], elen[:n1], off[:n1], ln[:n1], 1, 1)
+    v = blob.size / dt / 1e6
+    streams = args.streams or (STREAMS_PER_GPU if args.gpus == 1 else STREAMS_PER_GPU_SCALING)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
             "data": "synthetic",
-            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[1]), literal-only "
-                                   "encoding (1 PredictionMode + 1 Literal command)" % args.streams,
-                       "streams_per_gpu": args.streams, "stream_bytes": STREAM_BYTES,
-                       "sample": "each step decodes a bounded sample of %d of these streams on the host CPU" % n_sample},
+            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[%d]), literal-only "
+                                   "encoding (1 PredictionMode + 1 Literal command)" % (streams, 1 if args.gpus == 1 else 2),
+                       "streams_per_gpu": streams, "stream_bytes": STREAM_BYTES,
+                       "sample": "each step decodes the same fixed sample of %d of these streams on the host CPU; value = median step" % n_sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d streams per step, all %d host threads" % (n_sample, threads)},
+                             "sample": "%d streams per step, %d pinned host threads, median of %d steps (min %.3f s, max %.3f s)"
+                                       % (n_sample, threads, steps, min(ts), max(ts)),
+                             "single_thread_value": n1 * STREAM_BYTES / dt1 / 1e6},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+    return 0
+
+
+def _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, raw_blob, off, ln, steps):
+    """device-resident decode of one population: K steps timed with CUDA events on `stream`; returns (ms per step, decode-kernel
+    ms, bit-exact vs the raw input)"""
+    n = len(coff)
+    d_in = torch.from_numpy(comp).to(dev)
+    d_in_off, d_in_len = torch.from_numpy(coff.astype(np.int64)).to(dev), torch.from_numpy(clen.astype(np.int64)).to(dev)
+    d_out = torch.zeros(int(ln.sum()) + 256, dtype=torch.uint8, device=dev)
+    d_out_off, d_out_cap = torch.from_numpy(off.astype(np.int64)).to(dev), torch.from_numpy(ln.astype(np.int64)).to(dev)
+    d_out_len, d_status = torch.zeros(n, dtype=torch.int64, device=dev), torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def step():
+        eng.decode_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
+                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, d_in.numel(), 0, stream.cuda_stream)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ok = bool((d_status == 0).all()) and bool((d_out[: int(ln.sum())].cpu().numpy() == raw_blob[: int(ln.sum())]).all())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, eng.last_main_kernel_ms(), ok
+
+
+def _compact(out, eoff, out_len):
+    n = len(out_len)
+    pad = (out_len + np.uint64(15)) & ~np.uint64(15)
+    coff = np.zeros(n, np.uint64)
+    coff[1:] = np.cumsum(pad)[:-1]
+    comp = np.zeros(int(pad.sum()) + 64, np.uint8)
+    for i in range(n):
+        comp[int(coff[i]): int(coff[i] + out_len[i])] = out[int(eoff[i]): int(eoff[i] + out_len[i])]
+    return comp, coff, out_len.astype(np.uint64)
+
+
+def measure_populations(eng, torch, dev, stream, blob, off, ln, steps=3):
+    """the same raw streams under the other encodings.  Inputs are produced by the product's own GPU encoder (Z: the
+    library's greedy LZ77 command generator + the GPU command-list encoder)."""
+    import divans_b200
+    n = len(off)
+    cap = np.full(n, STREAM_BYTES + STREAM_BYTES // 2 + 70144, np.uint64)
+    eoff = np.arange(n, dtype=np.uint64) * cap[0]
+    out = np.zeros(int(cap.sum()), np.uint8)
+    pops = {}
+
+    def run(name, desc, opts, cmds=None):
+        if cmds is None:
+            out_len, status = eng.encode_batch_host(blob, off, ln, out, eoff, cap, opts)
+        else:
+            out_len, status = eng.encode_batch_host(cmds[0], cmds[1], cmds[2], out, eoff, cap, opts, cmds=True)
+        assert (status == 0).all(), name
+        comp, coff, clen = _compact(out, eoff, out_len)
+        ms, kms, ok = _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, blob, off, ln, steps)
+        pops[name] = {"encoding": desc, "ms_per_step": ms, "decode_kernel_ms": kms, "value": float(ln.sum()) / ms / 1e3, "unit": UNIT,
+                      "compressed_bytes": int(clen.sum()), "bit_exact": ok, "steps": steps}
+
+    run("Z_lz77_window16", "LZ77 command streams (greedy hash-chain matcher, window 16, min match 4; UTF8 context mode, mixing value 4): copy-dominated, like the reference's default compressor output",
+        divans_b200.encode_options(window_size=16), cmds=divans_b200.lz77_cmds_batch(blob, off, ln, 16, 2, 4))
+    run("L_dcm2", "literal-only, dynamic_context_mixing=2 (two priors mixed and the weights adapted per nibble)", divans_b200.encode_options(dynamic_context_mixing=2))
+    run("L_utf8", "literal-only, UTF8 context mode, mixing value 1", divans_b200.encode_options(literal_pred_mode=2, literal_mixing_value=1))
+    return pops
+
+
+def run_entropy(args, eng, rank, world, dev):
+    """BASELINE configs[4]: 1 MiB Bernoulli-bit streams, 128 per GPU, p in {0.5, 0.9, 0.99}; device-resident decode."""
+    import torch
+    import torch.distributed as dist
+    import divans_b200
+    from divans_b200 import synth
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    n, sb = 128, 1 << 20
+    res, tot_bytes, tot_ms = {}, 0.0, 0.0
+    for pr in (0.5, 0.9, 0.99):
+        blob, off, ln = synth.bernoulli_streams(n, sb, pr, seed=0xB17 + 1000 * rank)
+        cap = np.full(n, sb + sb // 2 + 70144, np.uint64)
+        eoff = np.arange(n, dtype=np.uint64) * cap[0]
+        out = np.zeros(int(cap.sum()), np.uint8)
+        out_len, status = eng.encode_batch_host(blob, off, ln, out, eoff, cap, divans_b200.encode_options())
+        assert (status == 0).all()
+        comp, coff, clen = _compact(out, eoff, out_len)
+        ms, kms, ok = _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, blob, off, ln, max(2, args.steps // 3))
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        res["p=%.2f" % pr] = {"ms_per_step": ms, "value": world * n * sb / ms / 1e3, "unit": UNIT, "ratio": float(clen.sum()) / (n * sb), "bit_exact": ok}
+        tot_bytes += world * n * sb
+        tot_ms += ms
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": tot_bytes / tot_ms / 1e3, "unit": UNIT, "n_gpus": world, "steps": max(2, args.steps // 3),
+                          "warmup": 2, "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
+                          "data": "synthetic",
+                          "config": {"workload": "entropy sweep (BASELINE configs[4]): %d x 1 MiB Bernoulli-bit streams per GPU, p in {0.5, 0.9, 0.99}, "
+                                                 "literal-only encoding" % n, "lanes_per_stream": args.lanes}, "sweep": res}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 
@@ -188,8 +330,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("DIVANS_B200_LPS", "8")), help="lanes per stream: 8 (default, 4 streams per warp), 16 or 32")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: 4096 at N=1, 8192 at N>1)")
+    ap.add_argument("--workload", default="text", choices=["text", "entropy"])
+    ap.add_argument("--skip-populations", action="store_true")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("DIVANS_B200_LPS", "0")), help="lanes per stream: 16 / 8 (v2 engine), 32 / 116 (round-1 kernels); 0 = by batch size")
     ap.add_argument("--cpu-sample", type=int, default=0, help="streams in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -211,7 +355,13 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if not args.streams:
+        args.streams = STREAMS_PER_GPU if world == 1 else STREAMS_PER_GPU_SCALING
+    if not args.lanes:
+        args.lanes = 16 if args.streams <= 4736 else 8      # 8 lanes per stream keep twice as many streams resident
     eng = divans_b200.Engine(local_rank, 0, args.lanes)
+    if args.workload == "entropy":
+        return run_entropy(args, eng, rank, world, dev)
     n = args.streams
     blob, off, ln = make_inputs(rank, n)
     comp, coff, clen, generator = encode_inputs(blob, off, ln, eng)
@@ -268,6 +418,11 @@ def main():
         torch.cuda.synchronize()
         main_ms.append(eng.last_main_kernel_ms())
     kern_ms = float(np.median(main_ms))
+
+    # ---- the other encodings of the same raw streams (rank 0's shard; device-resident, 3 steps each) ----
+    populations = None
+    if rank == 0 and not args.skip_populations:
+        populations = measure_populations(eng, torch, dev, stream, blob, off, ln)
 
     # ---- supplementary: the GPU encoder on the same shard, raw inputs resident in HBM (BASELINE configs[3] shape) ----
     d_raw = torch.from_numpy(blob).to(dev)
@@ -333,6 +488,48 @@ def main():
     assert all((st == 0).all() and (ol == STREAM_BYTES).all() for ol, st in results)
     assert (h_out_np_l[0][:out_bytes] == blob).all() and (h_out_np_l[1][:out_bytes] == blob).all()
 
+    # ---- N > 1: the sharded API.  Rank 0 owns the whole job's host batch (pinned), ShardedDecoder scatters it over NVLink,
+    # every rank decodes its byte-balanced shard in HBM, rank 0 gathers and copies the result to the host. ----
+    scattered = None
+    if world > 1:
+        sd = sharding.ShardedDecoder(eng, device=dev)
+        sizes = torch.tensor([comp.size, n], dtype=torch.int64, device=dev)
+        all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        g_comp = [torch.zeros(int(a[0]), dtype=torch.uint8, device=dev) if rank == 0 else None for a in all_sizes]
+        g_len = [torch.zeros(int(a[1]), dtype=torch.int64, device=dev) if rank == 0 else None for a in all_sizes]
+        g_off = [torch.zeros(int(a[1]), dtype=torch.int64, device=dev) if rank == 0 else None for a in all_sizes]
+        dist.gather(torch.from_numpy(comp).to(dev), g_comp if rank == 0 else None, dst=0)
+        dist.gather(torch.from_numpy(clen.astype(np.int64)).to(dev), g_len if rank == 0 else None, dst=0)
+        dist.gather(torch.from_numpy(coff.astype(np.int64)).to(dev), g_off if rank == 0 else None, dst=0)
+        if rank == 0:
+            base = np.concatenate([[0], np.cumsum([int(a[0]) for a in all_sizes])[:-1]])
+            job_blob = torch.cat(g_comp).cpu().pin_memory()
+            job_off = np.concatenate([g_off[r].cpu().numpy() + base[r] for r in range(world)])
+            job_len = np.concatenate([g_len[r].cpu().numpy() for r in range(world)])
+            job_cap = np.full(job_len.size, STREAM_BYTES, np.int64)
+            del g_comp
+        sc_steps = 3
+        for k in range(1 + sc_steps):
+            barrier()
+            t0 = time.perf_counter()
+            r = sd.decode(job_blob, job_off, job_len, job_cap) if rank == 0 else sd.decode()
+            barrier()
+            if k == 0:
+                if rank == 0:
+                    o, oo, ol, st_ = r
+                    assert bool((st_ == 0).all()) and bool((ol == STREAM_BYTES).all())
+                    assert bool((o[: n * STREAM_BYTES].numpy() == blob).all()), "sharded decode differs from the input"
+                t_sc = []
+            else:
+                t_sc.append(time.perf_counter() - t0)
+        if rank == 0:
+            scattered = {"value": float(job_len.size) * STREAM_BYTES / float(np.median(t_sc)) / 1e6, "unit": UNIT, "steps": sc_steps,
+                         "h2d_bytes_per_step": int(job_blob.numel()), "d2h_bytes_per_step": int(job_len.size) * STREAM_BYTES,
+                         "api": "divans_b200.sharding.ShardedDecoder: rank 0 holds the job's host batch; partition_by_bytes, NCCL send/recv scatter, "
+                                "device decode per rank, NCCL gather, one D2H on rank 0 (wall clock around the collective call)",
+                         "shard_bytes": sd.last.get("shard_bytes")}
+
     tt = torch.tensor([dev_ms, e2e_s * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
     uu = torch.tensor([float(out_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -347,19 +544,26 @@ def main():
         e2e_v = total_out * e2e_steps / (e2e_ms_max / 1e3) / 1e6
         alg_bytes = comp_bytes + out_bytes     # per launch of the decode kernel on this rank (B_alg)
         achieved = alg_bytes / (kern_ms / 1e3) / 1e9
-        traffic = None
+        # dram bytes of the decode kernel come from an ncu capture (profiles/traffic.json); they are only reported when that capture
+        # was made with the kernel version this library was built from
+        traffic, traffic_note = None, "no capture"
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("decode_kernel_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("kernel_version") == divans_b200.kernel_version() and int(tj.get("lanes_per_stream", 0)) == args.lanes and int(tj.get("streams", 0)) == n:
+                    traffic, traffic_note = tj.get("decode_kernel_dram_bytes_per_launch"), tj.get("source")
+                else:
+                    traffic_note = "profiles/traffic.json is for kernel %s (%s lanes, %s streams), this library is %s: not reported" % (
+                        tj.get("kernel_version"), tj.get("lanes_per_stream"), tj.get("streams"), divans_b200.kernel_version())
             except Exception:
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i16/u64", "data": "synthetic",
-            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[1]), literal-only "
-                                   "encoding (1 PredictionMode + 1 Literal command)" % n,
+            "config": {"workload": "%d independent 64 KiB synthetic-text divANS streams per GPU (BASELINE configs[%d]), literal-only "
+                                   "encoding (1 PredictionMode + 1 Literal command)" % (n, 1 if world == 1 else 2),
                        "streams_per_gpu": n, "stream_bytes": STREAM_BYTES, "compressed_bytes_per_gpu": comp_bytes,
                        "lanes_per_stream": args.lanes, "parallelism": "dp%d (streams sharded, no data-path collective)" % world,
                        "l2_policy": "inputs+outputs+model state per step (>0.39 GB + prior arena) exceed the 126 MB L2; no explicit flush",
@@ -369,8 +573,9 @@ def main():
                     "blocking_call_value": total_out / e2e_sync_ms_max * 1e3 / 1e6, "blocking_call_api": "divans_b200_decode_batch_host"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "dv::decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "dv::decode_kernel_v2<%d>" % args.lanes if args.lanes in (8, 16) else "dv::decode_kernel<%d>" % (args.lanes % 100), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                         "kernel_version": divans_b200.kernel_version(),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
         }
         line["encode"] = {"metric": "batched_encode_throughput_raw", "unit": UNIT, "steps": enc_steps, "n_gpus": 1,
@@ -380,9 +585,13 @@ def main():
                                               "model_kernel_ms": enc_model_ms, "compressed_bytes": comp_bytes},
                           "note": "rank 0's shard (BASELINE configs[3] shape: 4096 x 64 KiB), inputs and outputs resident in HBM; "
                                   "literal-only command generator (the brotli quality-11 command selection is out of scope)"}
+        if populations is not None:
+            line["populations"] = populations
+        if scattered is not None:
+            line["scattered_e2e"] = scattered
         if not args.skip_cpu and world == 1:
-            threads = os.cpu_count() or 1
-            ns = args.cpu_sample or max(64, 16 * threads)
+            threads = _pin_all_cores()
+            ns = args.cpu_sample or 2048
             cb, cpu_out = cpu_baseline(comp, coff, clen, blob, off, ln, ns, threads)
             nn = min(ns, n)
             cb["gpu_bit_exact_vs_oracle"] = bool((cpu_out[: nn * STREAM_BYTES] == h_out_np[: nn * STREAM_BYTES]).all())

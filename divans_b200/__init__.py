@@ -39,7 +39,7 @@ BATCH_SYMBOLS = [
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
     "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device", "divans_b200_ir_to_cmds",
-    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait", "divans_b200_lz77_cmds_batch",
+    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait", "divans_b200_lz77_cmds_batch", "divans_b200_kernel_version",
 ]
 
 
@@ -79,6 +79,7 @@ def load_library():
     L.divans_b200_destroy.argtypes = [vp]
     L.divans_b200_last_error.argtypes = [vp]
     L.divans_b200_last_error.restype = ctypes.c_char_p
+    L.divans_b200_kernel_version.restype = ctypes.c_char_p
     L.divans_b200_launch_count.argtypes = [vp]
     L.divans_b200_launch_count.restype = ctypes.c_uint64
     L.divans_b200_last_kernel_ms.argtypes = [vp]
@@ -151,6 +152,10 @@ def ir_to_cmds(text):
     if rc != DIVANS_SUCCESS:
         raise ValueError("IR parse failed")
     return out.tobytes(), int(win.value)
+
+
+def kernel_version():
+    return load_library().divans_b200_kernel_version().decode()
 
 
 def lz77_cmds_batch(blob, in_off, in_len, window=16, pred_mode=2, mixing_value=4, n_threads=None):

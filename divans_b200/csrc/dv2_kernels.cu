@@ -1,37 +1,33 @@
-// dv8_kernels.cu -- stream decoder of the 8-lane engine (dv8_core.cuh): persistent warps, FOUR streams per warp in lock step,
-// work pulled from a global counter.  Same framing pre-pass (dv_kernels.cu) and the same command state machine
-// (dv_engine_kernel.cuh, transition<false, true>) as the 16/32-lane decoders.
-#include "dv8_core.cuh"
+// dv2_kernels.cu -- stream decoder of the v2 engine (dv2_core.cuh): persistent warps, every warp runs 32 / LPG streams in
+// lock step (LPG = 16: two, LPG = 8: four), work pulled from a global counter.  Same framing pre-pass (dv_kernels.cu) and
+// the same command state machine (dv_engine_kernel.cuh, transition<false, true>) as the round-1 decoders.
+#include "dv2_core.cuh"
 
 namespace dv {
 
-constexpr int DEC8_BLOCK_THREADS = 32;          // one warp = 4 streams per block: blocks spread evenly over the SMs
-constexpr int DEC8_MIN_BLOCKS = 16;             // 16 warps = 64 streams per SM (9472 per B200), <= 128 registers
+constexpr int DEC2_BLOCK_THREADS = 32;          // one warp per block: blocks spread evenly over the SMs
+constexpr int DEC2_MIN_BLOCKS = 16;             // 16 warps per SM, <= 128 registers
 
-// a slot's generation wrapped (every 255 streams): forget every tag
-static __device__ __noinline__ void clear_tags(const G2 g, uint8_t *slot) {
-    uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_TAGS_HI);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (uint32_t i = (uint32_t)g.l16; i < (uint32_t)(2 * LIT_TABLE_CDFS / 16); i += (uint32_t)g.nl) p[i] = z;
-    __syncwarp(g.gmask);
-}
-
-__global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_kernel8(DecodeParams p) {
+template <int LPG, bool PF>
+__global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_kernel_v2(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
+    // one dummy word per lane behind the groups' cold state: destination of the L1-touching async copies (dv2_core.cuh)
+    const uint32_t smem_dummy = (uint32_t)__cvta_generic_to_shared(smem + (DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2) + 4u * threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
-    const int group_in_block = warp_in_block * 4 + (lane >> 3);
-    const uint32_t slot = blockIdx.x * (DEC8_BLOCK_THREADS / 8) + group_in_block;
+    constexpr int GPW = 32 / LPG;
+    const int group_in_block = warp_in_block * GPW + lane / LPG;
+    const uint32_t slot = blockIdx.x * (DEC2_BLOCK_THREADS / LPG) + group_in_block;
     G2 g;
-    g.l16 = lane & 7;
-    g.shift = lane & 24;
-    g.gmask = 0xffu << (lane & 24);
-    g.store0 = (lane & 7) == 0;
-    g.nl = 8;
+    g.l16 = lane & (LPG - 1);
+    g.shift = lane & ~(LPG - 1);
+    g.gmask = (LPG == 16 ? 0xffffu : 0xffu) << g.shift;
+    g.store0 = g.l16 == 0;
+    g.nl = LPG;
 
     St s;
     s.slot = p.arena + (uint64_t)slot * SLOT_STRIDE;
-    s.c = reinterpret_cast<Cold *>(smem + group_in_block * SMEM_BYTES_PER_GROUP8);
+    s.c = reinterpret_cast<Cold *>(smem + group_in_block * SMEM_BYTES_PER_GROUP_V2);
     s.tables = p.tables;
     s.state = S_IDLE;
     s.c->desired_context_mixing = 0; s.c->desired_prior_depth = 0; s.c->desired_force_stride = 9; s.c->desired_do_context_map = true;
@@ -43,7 +39,7 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
     s.gen = 0;
     st_reset(s);
     coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0; coder_init_dec(s.c->oth, nullptr, 0);
-    Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.sym = 0; nx.mix_hi = false; nx.tag = nullptr;
+    Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.sym = 0; nx.mix_hi = false; nx.tagged = false;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(s.slot + OFF_MISC), (uint32_t)MISC_CDFS);   // incl. the dummy CDF
     bool exhausted = false;
 
@@ -54,7 +50,7 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
         if (__any_sync(FULL, want)) {
             uint32_t v = 0;
             if (want && g.store0) v = atomicAdd(p.work_counter, 1u);
-            v = __shfl_sync(FULL, v, 0, 8);
+            v = __shfl_sync(FULL, v, 0, LPG);
             if (want) {
                 if (v >= p.n_streams) exhausted = true;
                 else if (p.status[v] != ST_OK) { if (g.store0) p.out_len[v] = 0; }   // framing / CRC failure: stay idle, fetch again
@@ -67,12 +63,19 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
                     uint64_t cap = p.out_cap[v];
                     s.c->out_cap = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap; s.out_pos = 0;
                     s.c->ring_len = 1u << in[5];
-                    reset_slot(g, s.slot, s.c->bitmaps);
+                    reset_slot_v2(g, s.slot, s.c->bitmaps);
                     st_reset(s);
-                    // a new generation: every literal prior of the slot reads as the default CDF until this stream writes it
+                    // a new generation: every literal prior of the slot reads as the default CDF until this stream writes it.  The
+                    // tables are wiped when the 16-bit generation wraps, or when an earlier user of the slot (a stream with
+                    // wrapping speeds, in any engine) may have left elements that use their sign bits
+                    uint32_t *hdr = reinterpret_cast<uint32_t *>(s.slot + OFF_HDR);
                     uint32_t ctr = s.c->gen_ctr + 1;
-                    if ((ctr & 0xffu) == 0) { clear_tags(g, s.slot); ctr++; }
-                    s.c->gen_ctr = ctr; s.gen = ctr & 0xffu;
+                    if ((ctr & 0xffffu) == 0 || hdr[1] != 0) {
+                        v2_clear_literal_tables(g, s.slot);
+                        if (g.store0) hdr[1] = 0;
+                        if ((ctr & 0xffffu) == 0) ctr++;
+                    }
+                    s.c->gen_ctr = ctr; s.gen = ctr & 0xffffu;
                     coder_init_dec(s.cur, reinterpret_cast<const uint32_t *>(pl), pay0 >> 2);   // command stream (CMD_CODER, codec/interface.rs:49)
                     coder_init_dec(s.c->oth, reinterpret_cast<const uint32_t *>(pl + (((uint64_t)pay0 + 15) & ~15ull)), pay1 >> 2);   // literal stream (LIT_CODER, :50)
                     enter_cmd_type<false>(s, nx);
@@ -84,14 +87,14 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
         // ---- whole literal bytes while every group is at a byte boundary of a literal (or out of work) ----
         const bool lit = s.state == S_LIT_HI;
         if (__all_sync(FULL, lit || (exhausted && s.state == S_IDLE)) && __any_sync(FULL, lit)) {
-            literal_fast8(s, nx, g, lit);
+            literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy);
             if (lit) {
                 if (s.cur.underflow) s.status = ST_NEED_INPUT;
                 if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); enter_cmd_type<false>(s, nx); }
                 if (s.status != ST_OK) {
                     if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
                     s.state = S_IDLE; s.status = ST_OK;
-                    nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tag = nullptr;
+                    nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tagged = false;
                     coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0;
                 }
             }
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
         }
         // ---- one nibble per group ----
         const bool busy = s.state != S_IDLE;
-        const int sym = nibble_core8(s, nx, g);
+        const int sym = nibble_core_v2<LPG>(s, nx, g);
         // ---- per-group scalar state machines (divergent) ----
         if (busy) {
             if (s.cur.underflow) s.status = ST_NEED_INPUT;
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
                 if (s.status == ST_OK && s.c->oth.underflow) s.status = ST_NEED_INPUT;
                 if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
                 s.state = S_IDLE; s.status = ST_OK;
-                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tag = nullptr;
+                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tagged = false;
                 coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0;
             }
         }
@@ -116,15 +119,20 @@ __global__ void __launch_bounds__(DEC8_BLOCK_THREADS, DEC8_MIN_BLOCKS) decode_ke
     if (g.store0) *reinterpret_cast<uint32_t *>(s.slot + OFF_HDR) = s.c->gen_ctr;
 }
 
-void launch_decode8(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
-    size_t smem = (size_t)(DEC8_BLOCK_THREADS / 8) * SMEM_BYTES_PER_GROUP8;
-    decode_kernel8<<<n_blocks, DEC8_BLOCK_THREADS, smem, st>>>(p);
+template <int LPG> static size_t smem_v2() { return (size_t)(DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2 + 4 * DEC2_BLOCK_THREADS; }
+template <int LPG, bool PF> static void launch_v2(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
+    decode_kernel_v2<LPG, PF><<<n_blocks, DEC2_BLOCK_THREADS, smem_v2<LPG>(), st>>>(p);
 }
-int decode_max_blocks_per_sm8() {
+template <int LPG> static int max_blocks_v2() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel8, DEC8_BLOCK_THREADS, (size_t)(DEC8_BLOCK_THREADS / 8) * SMEM_BYTES_PER_GROUP8);
-    return nb < DEC8_MIN_BLOCKS ? nb : DEC8_MIN_BLOCKS;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel_v2<LPG, false>, DEC2_BLOCK_THREADS, smem_v2<LPG>());
+    return nb;
 }
-int decode_groups_per_block8() { return DEC8_BLOCK_THREADS / 8; }
+void launch_decode_v2(int lanes_per_stream, bool prefetch, const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
+    if (lanes_per_stream == 8) { if (prefetch) launch_v2<8, true>(p, n_blocks, st); else launch_v2<8, false>(p, n_blocks, st); }
+    else { if (prefetch) launch_v2<16, true>(p, n_blocks, st); else launch_v2<16, false>(p, n_blocks, st); }
+}
+int decode_max_blocks_per_sm_v2(int lanes_per_stream) { return lanes_per_stream == 8 ? max_blocks_v2<8>() : max_blocks_v2<16>(); }
+int decode_groups_per_block_v2(int lanes_per_stream) { return DEC2_BLOCK_THREADS / lanes_per_stream; }
 
 }  // namespace dv

@@ -35,7 +35,10 @@ struct divans_b200_ctx {
     int sm_count = 0;
     uint32_t max_resident = 0;       // slots in the arena
     cudaStream_t stream = nullptr;
-    uint8_t *d_arena = nullptr; size_t arena_slots = 0;
+    uint8_t *d_arena = nullptr; size_t arena_slots = 0;   // 16 MiB aligned view of d_arena_raw
+    uint8_t *d_arena_raw = nullptr;
+    bool prefetch = false;           // v2 engine: touch the candidate priors of the next nibble (env DIVANS_B200_PREFETCH, default off)
+    int engine = 0;                  // 0: v2 (dv2_kernels.cu, lanes 16 or 8), 1: round-1 kernels (dv_kernels.cu, lanes 16 or 32)
     uint8_t *d_tables = nullptr;
     uint32_t *d_counter = nullptr;
     uint64_t *d_nibbles = nullptr;
@@ -95,7 +98,11 @@ static bool grow(divans_b200_ctx *ctx, T **p, size_t *cap, size_t need) {
 extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream) {
     divans_b200_ctx *ctx = new divans_b200_ctx();
     ctx->device = device;
-    ctx->lanes_per_stream = lanes_per_stream == 16 ? 16 : (lanes_per_stream == 32 ? 32 : 8);   // default: the 8-lane engine
+    // 16 (default, also 0): v2 engine, two streams per warp; 8: v2 engine, four streams per warp; 32: the round-1 kernel with one
+    // warp per stream; 116: the round-1 16-lane kernel (kept for A/B measurements)
+    ctx->engine = (lanes_per_stream == 32 || lanes_per_stream == 116) ? 1 : 0;
+    ctx->lanes_per_stream = lanes_per_stream == 8 ? 8 : (lanes_per_stream == 32 ? 32 : 16);
+    { const char *e = getenv("DIVANS_B200_PREFETCH"); ctx->prefetch = e && atoi(e) != 0; }
     cudaDeviceProp prop;
     if (!ck(ctx, cudaSetDevice(device), "cudaSetDevice") || !ck(ctx, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
         fprintf(stderr, "divans_b200: no usable CUDA device %d -- this library has no CPU path\n", device);
@@ -116,14 +123,14 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
               ck(ctx, cudaMalloc((void **)&ctx->d_nibbles, 64), "cudaMalloc(nibbles)") &&
               ck(ctx, cudaMemset(ctx->d_nibbles, 0, 64), "cudaMemset");
     if (!ok) { delete ctx; return nullptr; }
-    int per_sm = ctx->lanes_per_stream == 8 ? decode_max_blocks_per_sm8() : ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
+    int per_sm = ctx->engine == 0 ? decode_max_blocks_per_sm_v2(ctx->lanes_per_stream) : ctx->lanes_per_stream == 16 ? decode_max_blocks_per_sm16() : decode_max_blocks_per_sm32();
     if (per_sm < 1) per_sm = 1;
-    uint32_t groups_per_block = ctx->lanes_per_stream == 8 ? (uint32_t)decode_groups_per_block8() : DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
+    uint32_t groups_per_block = ctx->engine == 0 ? (uint32_t)decode_groups_per_block_v2(ctx->lanes_per_stream) : DECODE_BLOCK_THREADS / ctx->lanes_per_stream;
     ctx->groups_per_block = groups_per_block;
     uint32_t auto_res = (uint32_t)ctx->sm_count * (uint32_t)per_sm * groups_per_block;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    uint32_t mem_cap = (uint32_t)((free_b * 7 / 10) / SLOT_STRIDE);   // leave room for batch buffers
+    uint32_t mem_cap = (uint32_t)((free_b * 8 / 10) / SLOT_STRIDE);   // leave room for batch buffers
     if (auto_res > mem_cap) auto_res = mem_cap;
     ctx->max_resident = max_resident ? (max_resident < auto_res ? max_resident : auto_res) : auto_res;
     if (ctx->max_resident < groups_per_block) ctx->max_resident = groups_per_block;
@@ -137,7 +144,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
-    cudaFree(ctx->d_arena); cudaFree(ctx->d_tables); cudaFree(ctx->d_counter); cudaFree(ctx->d_nibbles);
+    cudaFree(ctx->d_arena_raw); cudaFree(ctx->d_tables); cudaFree(ctx->d_counter); cudaFree(ctx->d_nibbles);
     cudaFree(ctx->d_frame); cudaFree(ctx->d_payload); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_meta);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -157,6 +164,9 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+// bumped whenever a decode kernel changes: profiles/traffic.json (an ncu capture) is only quoted by bench.py for the version it measured
+#define DV_KERNEL_VERSION "r2.3-v2-signtags"
+extern "C" const char *divans_b200_kernel_version(void) { return DV_KERNEL_VERSION; }
 extern "C" const char *divans_b200_last_error(divans_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" uint64_t divans_b200_launch_count(divans_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" float divans_b200_last_kernel_ms(divans_b200_ctx *ctx) {
@@ -179,11 +189,11 @@ extern "C" DivansResult divans_b200_synchronize(divans_b200_ctx *ctx) {
 
 static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
     if (slots <= ctx->arena_slots) return DIVANS_SUCCESS;
-    if (ctx->d_arena) { cudaFree(ctx->d_arena); ctx->d_arena = nullptr; ctx->arena_slots = 0; }
-    CK(cudaMalloc((void **)&ctx->d_arena, slots * SLOT_STRIDE));
-    // generation tags, context table and slot header must start out as zeros (tag 0 = never valid); everything else in a slot
-    // is initialised by the kernels
-    CK(cudaMemset2D(ctx->d_arena + OFF_TAGS_HI, SLOT_STRIDE, 0, PERSISTENT_BYTES, slots));
+    if (ctx->d_arena_raw) { cudaFree(ctx->d_arena_raw); ctx->d_arena_raw = ctx->d_arena = nullptr; ctx->arena_slots = 0; }
+    CK(cudaMalloc((void **)&ctx->d_arena_raw, (slots + 1) * SLOT_STRIDE));
+    ctx->d_arena = reinterpret_cast<uint8_t *>(((uintptr_t)ctx->d_arena_raw + SLOT_STRIDE - 1) & ~(uintptr_t)(SLOT_STRIDE - 1));   // slots are 16 MiB aligned (dv_common.cuh)
+    // the v2 engine reads literal priors it has never written (tag 0 = never valid) and keeps a header per slot: zero it all once
+    CK(cudaMemset(ctx->d_arena, 0, slots * SLOT_STRIDE));
     ctx->arena_slots = slots;
     return DIVANS_SUCCESS;
 }
@@ -220,7 +230,7 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     launch_frame(fp, ctx->d_payload, (uint64_t)ctx->payload_cap, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
-    if (!skip_decode) { if (ctx->lanes_per_stream == 8) launch_decode8(dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
+    if (!skip_decode) { if (ctx->engine == 0) launch_decode_v2(ctx->lanes_per_stream, ctx->prefetch, dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;

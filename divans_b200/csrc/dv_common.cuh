@@ -32,18 +32,21 @@ constexpr uint64_t MISC_CDFS = 128;
 constexpr uint64_t OFF_LCM = OFF_MISC + MISC_CDFS * CDF_BYTES;   // literal context map (== the recycled PredictionMode buffer)
 constexpr uint64_t OFF_MIX = OFF_LCM + 16384;                     // mixing mask
 constexpr uint64_t OFF_DCM = OFF_MIX + 8192;                      // distance context map
-// 8-lane engine (dv8_*.cu*): one generation tag byte per literal prior (a prior whose tag differs from the stream's
-// generation reads as the default CDF [4,8,...,64] and is tagged when it is first written: no per-stream initialisation of
-// the 12.6 MB of literal priors, not even of the reachable slabs), the per-stream context table
-// T2[byte][lut1 class] = literal_context_map[block type][lut0[byte] | class] (8 classes, codec/literal.rs:87-117 in one
-// lookup), and a small header that survives from launch to launch (generation counter).
-constexpr uint64_t OFF_TAGS_HI = OFF_DCM + 1024;
-constexpr uint64_t OFF_TAGS_LO = OFF_TAGS_HI + LIT_TABLE_CDFS;
-constexpr uint64_t OFF_T2 = OFF_TAGS_LO + LIT_TABLE_CDFS;
-constexpr uint64_t OFF_HDR = OFF_T2 + 2048;
+// v2 engine (dv2_*.cu*).  Literal priors carry a 16-bit GENERATION TAG in the free sign bits of their 16 elements (element i
+// holds bit i of the tag in its bit 15; adaptive values stay below 2^15 for every speed the fast paths accept): a prior whose
+// tag differs from the generation of the stream that owns the slot reads as the default CDF [4,8,...,64] and takes the
+// stream's tag with its first write -- no per-stream initialisation of the 12.6 MB of literal priors, not even of the
+// reachable slabs (round 1 wrote 640 KB of defaults per 64 KiB stream).  Streams whose speeds could wrap an i16 counter
+// (they need all 16 bits) switch the slot to untagged priors (dv_engine.cuh: v2_make_untagged).
+// OFF_T2: the per-stream context table T2[byte][class of the byte before] = literal_context_map[block type][lut0[byte] | class]
+// (8 classes = the values of lut1, codec/literal.rs:87-117 in one lookup; each entry also carries the class of `byte` itself); OFF_HDR: what survives from launch to launch (generation counter, dirty flag).
+constexpr uint64_t OFF_T2 = OFF_DCM + 1024;           // 2048 x u16: context | (class of the byte itself) << 8
+constexpr uint64_t OFF_HDR = OFF_T2 + 4096;           // u32 generation counter, u32 "literal tables may hold untagged 16-bit values"
 constexpr uint64_t OFF_SLOT_END = OFF_HDR + 64;
-constexpr uint64_t SLOT_STRIDE = ((OFF_SLOT_END + 4095) / 4096) * 4096;
-constexpr uint64_t PERSISTENT_BYTES = OFF_SLOT_END - OFF_TAGS_HI;   // zeroed once when the arena is allocated
+// Slots are 16 MiB apart and the arena is 16 MiB aligned: any address inside a slot is (high word of the slot : low word of
+// the slot + offset), i.e. ONE 32-bit add in the decode loop instead of 64-bit pointer arithmetic (dv2_core.cuh).
+constexpr uint64_t SLOT_STRIDE = 16ull << 20;
+static_assert(OFF_SLOT_END <= SLOT_STRIDE, "slot layout exceeds the slot stride");
 // low-nibble prior index of the 8-lane engine: [which][index_c >> 4][index_b][index_c & 15]
 __host__ __device__ __forceinline__ uint32_t lit_index_lo(uint32_t which, uint32_t index_c, uint32_t index_b) {
     return (which << 16) | ((index_c >> 4) << 12) | (index_b << 4) | (index_c & 15u);

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
     st_reset(s);
     uint32_t *const dummy_log = p.sf_dummy + slot;
     coder_init_enc(s.cur, dummy_log); coder_init_enc(s.c->oth, dummy_log);
-    Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tag = nullptr; nx.sym = 0; nx.mix_hi = false;
+    Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tagged = false; nx.sym = 0; nx.mix_hi = false;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(s.slot + OFF_MISC), (uint32_t)MISC_CDFS);
     bool exhausted = false;
     const uint32_t per_stream = p.cmd_cap + p.lit_cap;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
                     p.sf_counts[2 * v] = s.status == ST_OK ? nc : 0; p.sf_counts[2 * v + 1] = s.status == ST_OK ? nl : 0;
                 }
                 s.state = S_IDLE; s.status = ST_OK;
-                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tag = nullptr; nx.sym = 0;
+                nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.tagged = false; nx.sym = 0;
                 coder_init_enc(s.cur, dummy_log);
             }
         }

@@ -54,7 +54,7 @@ struct Next {
     int speed;         // inc | lim<<16 for `cdf`; SPK_NONE = read-only (mm_opts == 2: literal.rs:213-216,252-256)
     int sym;           // ENC: symbol to code
     bool mix_hi;       // mixing: which of the two weight sets / cm speeds (true = high nibble)
-    uint8_t *tag;      // 8-lane engine: generation tag of `cdf` (literal tables; nullptr = the prior is always initialised)
+    bool tagged;       // v2 engine: `cdf` is a literal prior that carries a generation tag in its sign bits (dv_common.cuh)
 };
 // A blend with inc 0 and an unreachable limit leaves the CDF bit-identical: "do not adapt" without a branch.
 #define SPK_NONE sp_pack(0, 0x7fff)
@@ -93,7 +93,10 @@ struct Cold {
     uint32_t lit_log_cap;                    // encoder: capacity (entries) of the literal coder's log
     uint32_t sidx;                           // stream index being processed
     uint32_t model_rev;                      // DecodeParams::model_rev
-    uint32_t gen_ctr;                        // 8-lane engine: streams this slot has hosted (generation of the literal-prior tags)
+    uint32_t gen_ctr;                        // v2 engine: streams this slot has hosted (generation of the literal-prior tags)
+    uint32_t lit_total;                      // v2 engine: length of the literal in flight
+    bool lit_quirk;                          // v2 engine: the literal began within 8 bytes of the ring start (last_8_literals is not a plain mirror of the output)
+    bool pm_seen;                            // a PredictionMode command of THIS stream has written the mixing mask
     bool t2_dirty;                           // 8-lane engine: the slot's context table (OFF_T2) does not match lcm / mode / block type
     // encoder
     CmdIn in;
@@ -123,7 +126,8 @@ struct St {
     int status;
     uint32_t f0, f1, f2, f3;                 // scratch of the command being coded (meaning depends on the state)
     uint32_t lit_left, lit_ctx, lit_h;       // literal in flight
-    uint32_t gen;                            // 8-lane engine: tag value of literal priors that belong to the current stream (1..255)
+    uint32_t gen;                            // v2 engine: 16-bit tag of the literal priors that belong to the current stream (never 0)
+    bool tagged;                             // v2 engine: literal priors carry tags (false after v2_make_untagged)
 };
 
 // arena accessors
@@ -254,13 +258,70 @@ static __device__ __noinline__ int scan_literal_config(const G2 g, uint8_t *slot
     return (present & (present - 1)) == 0 ? (__ffs(present) - 1) : -1;
 }
 
+// v2 engine: every literal prior of the slot becomes "never written" (tag 0 never matches a generation)
+static __device__ __noinline__ void v2_clear_literal_tables(const G2 g, uint8_t *slot) {
+    uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_LIT_HI);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = (uint32_t)g.l16; i < (uint32_t)(2 * LIT_TABLE_CDFS * CDF_BYTES / 16); i += (uint32_t)g.nl) p[i] = z;
+    __syncwarp(g.gmask);
+}
+// v2 engine: a stream whose speeds can wrap i16 counters needs all 16 bits of every element.  Priors of the current generation
+// lose their tag bits, every other prior becomes the default CDF, and every slab is marked initialised (the bitmaps the
+// round-1 engine uses).  From here on the stream's literal priors are plain i16 arrays.
+static __device__ __noinline__ void v2_make_untagged(const G2 g, uint8_t *slot, uint32_t *bitmaps, uint32_t gen) {
+    uint32_t *p = reinterpret_cast<uint32_t *>(slot + OFF_LIT_HI);
+    const uint32_t n_cdf = (uint32_t)(2 * LIT_TABLE_CDFS);
+    for (uint32_t c = (uint32_t)g.l16; c < n_cdf; c += (uint32_t)g.nl) {     // one CDF (8 words) per lane and step
+        uint32_t w[8], tag = 0;
+        for (int k = 0; k < 8; k++) { w[k] = p[(size_t)c * 8 + k]; tag |= ((w[k] >> 15) & 1u) << (2 * k) | ((w[k] >> 31) & 1u) << (2 * k + 1); }
+        const bool mine = tag == gen;
+        for (int k = 0; k < 8; k++) p[(size_t)c * 8 + k] = mine ? (w[k] & 0x7fff7fffu) : ((uint32_t)(8 * k + 4) | ((uint32_t)(8 * k + 8) << 16));
+    }
+    __syncwarp(g.gmask);
+    for (uint32_t i = (uint32_t)g.l16; i < 48; i += (uint32_t)g.nl) bitmaps[i] = 0xffffffffu;
+    if (g.store0) reinterpret_cast<uint32_t *>(slot + OFF_HDR)[1] = 1u;       // the next stream must not trust sign bits in this slot
+    __syncwarp(g.gmask);
+}
+
 // fresh arena state for a new stream: zero the maps (ffi/alloc_util.rs:70-99), clear slab bitmaps, default the dense priors
+// Slot header words (OFF_HDR, persistent): [0] generation counter, [1] literal tables may hold untagged 16-bit values,
+// [2] literal-context-map bytes written since the map was last zeroed, [3] the mixing mask holds values of an earlier stream.
 static __device__ __noinline__ void reset_slot(const G2 g, uint8_t *slot, uint32_t *bitmaps) {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_LCM);
     for (uint32_t i = g.l16; i < (16384 + 8192 + 1024) / 16; i += g.nl) p[i] = z;   // lcm, mix, dcm are contiguous
     for (uint32_t i = g.l16; i < 65; i += g.nl) bitmaps[i] = 0;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(slot + OFF_MISC), (uint32_t)MISC_CDFS);
+    if (g.store0) { uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR); hdr[2] = 0; hdr[3] = 0; }
+    __syncwarp(g.gmask);
+}
+// v2 engine: the same fresh state without streaming 25 KB of zeros through L2 per stream.  Only the part of the literal context
+// map that earlier streams wrote is zeroed (header word 2: 64 bytes for the usual one-block-type map); the mixing mask is
+// left alone until it is needed -- a PredictionMode command rewrites all 8192 values, a literal that arrives before any
+// such command zeroes it first (v2_mix_before_use).
+static __device__ __noinline__ void reset_slot_v2(const G2 g, uint8_t *slot, uint32_t *bitmaps) {
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint32_t lcm16 = (min(hdr[2], 16384u) + 15u) / 16u;
+    uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_LCM);
+    for (uint32_t i = g.l16; i < lcm16; i += g.nl) p[i] = z;
+    uint4 *d = reinterpret_cast<uint4 *>(slot + OFF_DCM);
+    for (uint32_t i = g.l16; i < 1024 / 16; i += g.nl) d[i] = z;
+    for (uint32_t i = g.l16; i < 65; i += g.nl) bitmaps[i] = 0;
+    store_default_cdfs(g, reinterpret_cast<int16_t *>(slot + OFF_MISC), (uint32_t)MISC_CDFS);
+    __syncwarp(g.gmask);
+    if (g.store0) hdr[2] = 0;
+    __syncwarp(g.gmask);
+}
+static __device__ __noinline__ void v2_mix_before_use(const G2 g, uint8_t *slot) {
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR);
+    if (hdr[3] != 0) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_MIX);
+        for (uint32_t i = g.l16; i < 8192 / 16; i += g.nl) p[i] = z;
+        __syncwarp(g.gmask);
+        if (g.store0) hdr[3] = 0;
+    }
     __syncwarp(g.gmask);
 }
 

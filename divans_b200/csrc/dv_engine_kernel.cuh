@@ -29,7 +29,7 @@ __device__ __forceinline__ int load_cmd(St &s) {
 template <bool ENC>
 __device__ __forceinline__ void enter_cmd_type(St &s, Next &nx) {
     s.state = S_CMD_TYPE;
-    nx.cdf = A_misc(s, MI_CC + (int)(s.c->last_4_states >> 4)); nx.cdf2 = nullptr; nx.speed = SPK_ROCKET; nx.tag = nullptr;
+    nx.cdf = A_misc(s, MI_CC + (int)(s.c->last_4_states >> 4)); nx.cdf2 = nullptr; nx.speed = SPK_ROCKET; nx.tagged = false;
     if (ENC) {
         if (s.c->in.pos < s.c->in.n_cmds) nx.sym = load_cmd<ENC>(s);
         else nx.sym = 0xf;   // end of stream nibble (codec/mod.rs:143-148, flush :424-455)
@@ -68,8 +68,8 @@ __device__ __forceinline__ void enter_lit_nibble(St &s, Next &nx) {
     int16_t *np = A_lit(s, HIGH) + (size_t)flat * 16;
     const bool ro = (cfg & 0x800) != 0;
     nx.mix_hi = HIGH;
-    // (the never-adapted flat prior of mixing value 2 has no tag; with dynamic context mixing the stride prior is still READ)
-    nx.tag = (V2 && (s.mixing_trait || !ro)) ? s.slot + (HIGH ? OFF_TAGS_HI : OFF_TAGS_LO) + flat : nullptr;
+    // (the never-adapted flat prior of mixing value 2 is MI_FLAT, untagged; with dynamic context mixing the stride prior is still READ)
+    nx.tagged = V2 && s.tagged && (s.mixing_trait || !ro);
     if (s.mixing_trait) {
         nx.cdf = np; nx.speed = ro ? SPK_NONE : s.ad_stride;
         nx.cdf2 = HIGH ? A_litcm(s) + (size_t)ctx * 16 : A_litcm(s) + (size_t)(256 + s.lit_h + 16 * ctx) * 16;
@@ -112,11 +112,13 @@ template <bool ENC, bool V2 = false>
 __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint32_t len) {
     if ((uint64_t)len > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
     if (!s.c->lit_slabs_ready) {
-        // 8-lane engine: literal priors carry generation tags and are defaulted on first touch -- nothing to initialise
-        int u = V2 ? scan_literal_config(g, s.slot, s.c->bitmaps, s.mixing_trait) : ensure_literal_slabs(g, s.slot, s.c->bitmaps, s.mixing_trait);
+        if (V2 && !s.c->pm_seen) v2_mix_before_use(g, s.slot);   // no PredictionMode command yet: the mask must read as zeros
+        // v2 engine: literal priors carry generation tags and read as the default CDF until first written: nothing to initialise
+        int u = (V2 && s.tagged) ? scan_literal_config(g, s.slot, s.c->bitmaps, s.mixing_trait) : ensure_literal_slabs(g, s.slot, s.c->bitmaps, s.mixing_trait);
         s.lit_cfg = u >= 0 ? mm_cfg((uint32_t)u) : -1; s.c->lit_slabs_ready = true;
     }
     s.l8 = reseed_last8(s);
+    s.c->lit_quirk = (s.out_pos & (s.c->ring_len - 1)) < 8u; s.c->lit_total = len;
     swap_coders(s);
     s.lit_left = len;
     if (ENC) {
@@ -149,7 +151,7 @@ __device__ __forceinline__ void obs_btype(St &s, int k, uint32_t bt) {   // code
 }
 
 template <bool ENC> __device__ __forceinline__ void set_next(Next &nx, int16_t *cdf, int speed, int sym) {
-    nx.cdf = cdf; nx.cdf2 = nullptr; nx.speed = speed; nx.tag = nullptr;
+    nx.cdf = cdf; nx.cdf2 = nullptr; nx.speed = speed; nx.tagged = false;
     if (ENC) nx.sym = sym;
 }
 
@@ -265,7 +267,10 @@ template <bool ENC> __device__ __forceinline__ void pm_map_store(St &s, Next &nx
     uint32_t cap = s.f2 ? 1024u : 16384u;
     if (s.f1 >= cap) { s.status = ST_FAIL; return; }   // IndexBeyondContextMapSize
     cmap_touch(s, val);
-    if (g.store0) (s.f2 ? A_dcm(s) : A_lcm(s))[s.f1] = (uint8_t)val;
+    if (g.store0) {
+        (s.f2 ? A_dcm(s) : A_lcm(s))[s.f1] = (uint8_t)val;
+        if (!s.f2) { uint32_t *hdr = reinterpret_cast<uint32_t *>(s.slot + OFF_HDR); if (s.f1 >= hdr[2]) hdr[2] = s.f1 + 1; }   // high-water mark (reset_slot_v2)
+    }
     s.f1++;
     enter_pm_map_mnemonic<ENC>(s, nx);
 }
@@ -483,7 +488,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
     } break;
     case S_PM_MAP_SECOND: pm_map_store<ENC>(s, nx, g, (s.lit_h << 4) | (uint32_t)nib); break;
     case S_PM_MIXVAL: {
-        if (g.store0) A_mix(s)[s.f1] = (uint8_t)nib;
+        if (g.store0) { A_mix(s)[s.f1] = (uint8_t)nib; if (s.f1 == 0) reinterpret_cast<uint32_t *>(s.slot + OFF_HDR)[3] = 1u; }
         if (++s.f1 == 8192) {   // obs_prediction_mode_context_map, codec/interface.rs:293-321
             uint32_t mixing_math = (s.f3 >> 1) & 3;
             s.c->mixing_param = mixing_math; s.mixing_trait = mixing_math > 1;
@@ -494,7 +499,9 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             s.c->ad_cm_lo = f8_pair_to_speed((uint32_t)(a >> 32) & 0xff, (uint32_t)(a >> 40) & 0xff);
             s.c->ad_cm_hi = f8_pair_to_speed((uint32_t)(a >> 48) & 0xff, (uint32_t)(a >> 56) & 0xff);
             s.speeds_small = speed_is_small(s.ad_stride) && speed_is_small(s.c->ad_cm_lo) && speed_is_small(s.c->ad_cm_hi);
-            s.c->lit_slabs_ready = false; s.c->t2_dirty = true;
+            if (V2 && !s.speeds_small && s.tagged) { v2_make_untagged(g, s.slot, s.c->bitmaps, s.gen); s.tagged = false; }
+            if (!V2 && !s.speeds_small && g.store0) reinterpret_cast<uint32_t *>(s.slot + OFF_HDR)[1] = 1u;   // elements may use their sign bits: the v2 engine must wipe before trusting tags
+            s.c->lit_slabs_ready = false; s.c->t2_dirty = true; s.c->pm_seen = true;
             if (ENC) s.c->in.pos++;
             enter_cmd_type<ENC>(s, nx);
         } else enter_pm_mixval<ENC>(s, nx);
@@ -516,8 +523,9 @@ __device__ __forceinline__ void st_reset(St &s) {
     s.ad_stride = s.c->ad_cm_lo = s.c->ad_cm_hi = SPK_MUD;
     s.c->w_lo.w0 = s.c->w_lo.w1 = 1; s.c->w_lo.norm = 1 << 14; s.c->w_hi = s.c->w_lo;
     s.speeds_small = true;   // MUD
+    s.tagged = true;
     s.c->mixing_param = 1; s.mixing_trait = false; s.c->lit_slabs_ready = false; s.lit_cfg = -1;
-    s.status = ST_OK; s.c->cur_is_lit = false; s.c->t2_dirty = true;
+    s.status = ST_OK; s.c->cur_is_lit = false; s.c->t2_dirty = true; s.c->pm_seen = false;
     s.f0 = s.f1 = s.f2 = s.f3 = 0; s.lit_left = s.lit_ctx = s.lit_h = 0;
     s.c->e0 = s.c->e1 = s.c->e2 = s.c->e3 = 0;
 }

@@ -9,9 +9,10 @@ void launch_frame(const FrameParams &p, uint8_t *payload, uint64_t payload_cap_b
 void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
 int decode_max_blocks_per_sm32();
-void launch_decode8(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);   // 8-lane engine: 4 streams per warp (dv8_kernels.cu)
-int decode_max_blocks_per_sm8();
-int decode_groups_per_block8();
+// v2 engine (dv2_kernels.cu), lanes_per_stream = 16 (two streams per warp) or 8 (four)
+void launch_decode_v2(int lanes_per_stream, bool prefetch, const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
+int decode_max_blocks_per_sm_v2(int lanes_per_stream);
+int decode_groups_per_block_v2(int lanes_per_stream);
 int decode_max_blocks_per_sm16();
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st);                  // reverse rANS + mux/CRC (2 launches)

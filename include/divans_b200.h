@@ -114,11 +114,15 @@ typedef struct divans_b200_ctx divans_b200_ctx;
 /* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
 
 /* device = CUDA ordinal; max_resident = cap on concurrently resident streams (0 = auto: sized to the GPU);
- * lanes_per_stream = 8 (default, also for 0: four streams per warp, two CDF elements per lane -- the fast engine), 16 (two
- * streams per warp, one element per lane) or 32 (one warp owns one stream, the upper half-warp mirrors the lower). */
+ * lanes_per_stream = 16 (default, also for 0: two streams per warp, one CDF element per lane), 8 (four streams per warp,
+ * two elements per lane: twice the resident streams, for batches beyond ~4700 streams) -- both the round-2 engine -- or
+ * 32 (round-1 kernel, one warp owns one stream, the upper half-warp mirrors the lower); 116 selects the round-1 16-lane
+ * kernel (A/B measurements). */
 divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream);
 void divans_b200_destroy(divans_b200_ctx *ctx);
 const char *divans_b200_last_error(divans_b200_ctx *ctx);
+/* version string of the decode kernels in this build (quoted next to profile-derived numbers) */
+const char *divans_b200_kernel_version(void);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */
 uint64_t divans_b200_launch_count(divans_b200_ctx *ctx);
 /* device time of the most recent decode/encode kernel(s) in milliseconds (CUDA events on the context stream) */

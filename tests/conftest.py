@@ -32,15 +32,16 @@ def golden():
 @pytest.fixture(scope="session")
 def engine():
     import divans_b200
-    eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "8")))   # default: the 8-lane engine (4 streams per warp)
+    eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "16")))   # default: the v2 engine, two streams per warp
     yield eng
     eng.close()
 
 
 @pytest.fixture(scope="session")
 def engine16():
+    # the other lane layout of the v2 engine: four streams per warp, two CDF elements per lane
     import divans_b200
-    eng = divans_b200.Engine(0, 64, 16)
+    eng = divans_b200.Engine(0, 64, 8)
     yield eng
     eng.close()
 

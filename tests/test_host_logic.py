@@ -126,6 +126,52 @@ def test_world_size_2_gloo_sharding():
     assert res[0][3] == res[1][3] == 5050.0 and res[0][4] == res[1][4] == 2.0
 
 
+def _sharded_worker(rank, world, port, q):
+    """world_size-2 gloo job: the root's host batch is scattered, decoded per rank (stand-in decoder: the CPU oracle), gathered"""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from divans_b200 import sharding, synth
+    from oracle import oracle_py as O
+
+    def oracle_decode(d_in, in_off, in_len, d_out, out_off, out_cap):
+        out, out_len, status = O.decode_batch(d_in.numpy(), in_off.numpy().astype(np.uint64), in_len.numpy().astype(np.uint64),
+                                              out_off.numpy().astype(np.uint64), out_cap.numpy().astype(np.uint64), 2)
+        d_out[: out.size] = torch.from_numpy(out)
+        return torch.from_numpy(out_len.astype(np.int64)), torch.from_numpy(status)
+
+    dec = sharding.ShardedDecoder(device="cpu", decode_fn=oracle_decode)
+    if rank == 0:
+        text = synth.text_corpus(1 << 16)
+        raws = [text[i * 900: i * 900 + 400 + 350 * (i % 7)] for i in range(23)] + [b""]
+        streams = [O.encode_raw(r, O.options(window_size=12)) for r in raws]
+        in_len = np.array([len(s) for s in streams], np.uint64)
+        in_off = np.concatenate([[0], np.cumsum(in_len)[:-1]]).astype(np.uint64)
+        out, out_off, out_len, status = dec.decode(np.frombuffer(b"".join(streams), np.uint8).copy(), in_off, in_len,
+                                                   np.array([len(r) + 5 for r in raws], np.uint64))
+        ok = bool((status == 0).all()) and all(out[int(o): int(o) + int(l)].numpy().tobytes() == r for o, l, r in zip(out_off, out_len, raws))
+        q.put((ok, dec.last["parts"], dec.last["shard_bytes"]))
+    else:
+        assert dec.decode() is None
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_decoder():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 311) % 1000)
+    ps = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    ok, parts, shard_bytes = q.get(timeout=180)
+    [p.join(60) for p in ps]
+    assert ok
+    assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == 24 and 0 < parts[0][1] < 24
+    assert abs(shard_bytes[0] - shard_bytes[1]) < 0.2 * sum(shard_bytes)      # balanced by compressed bytes
+
+
 def test_ir_front_end_matches_oracle_parser(oracle):
     """The product's C++ IR parser (divans_b200_ir_to_cmds) yields the same command-list blob as the oracle's parser --
     which is pinned to the reference by replaying the reference's testdata/*.ir fixtures (tests/test_oracle_kat.py)."""

@@ -10,7 +10,7 @@ from irfuzz import random_ir
 
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 import os
-eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "8")))
+eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "16")))
 text = synth.text_corpus(1 << 18)
 base = []
 for seed in range(16):

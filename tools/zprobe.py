@@ -6,7 +6,7 @@ from divans_b200 import synth
 from oracle import oracle_py as O
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 import os
-eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "8")))
+eng = divans_b200.Engine(0, 0, int(os.environ.get("DIVANS_B200_LPS", "16")))
 blob, off, ln = synth.text_streams(n, 65536, seed=3)
 raws = [blob[int(o):int(o + l)].tobytes() for o, l in zip(off, ln)]
 streams = [O.Commands.lz77(r, 16, 2, 4).encode(O.options(window_size=16)) for r in raws]
