@@ -39,7 +39,7 @@ BATCH_SYMBOLS = [
     "divans_b200_last_kernel_ms", "divans_b200_last_main_kernel_ms", "divans_b200_decode_batch_host", "divans_b200_decode_batch_device",
     "divans_b200_synchronize", "divans_b200_encode_options_default", "divans_b200_encode_batch_host",
     "divans_b200_encode_cmds_batch_host", "divans_b200_encode_batch_device", "divans_b200_ir_to_cmds",
-    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait", "divans_b200_lz77_cmds_batch", "divans_b200_kernel_version",
+    "divans_b200_decode_batch_host_async", "divans_b200_decode_batch_host_wait", "divans_b200_lz77_cmds_batch", "divans_b200_kernel_version", "divans_b200_last_lanes",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library():
     L.divans_b200_last_error.argtypes = [vp]
     L.divans_b200_last_error.restype = ctypes.c_char_p
     L.divans_b200_kernel_version.restype = ctypes.c_char_p
+    L.divans_b200_last_lanes.argtypes = [vp]
     L.divans_b200_launch_count.argtypes = [vp]
     L.divans_b200_launch_count.restype = ctypes.c_uint64
     L.divans_b200_last_kernel_ms.argtypes = [vp]
@@ -194,9 +195,10 @@ def encode_options(**kw):
 
 
 class Engine:
-    """Batch engine bound to one GPU.  ``lanes_per_stream``: 32 = one warp owns one stream, 16 = two streams per warp."""
+    """Batch engine bound to one GPU.  ``lanes_per_stream``: 0 = by batch size (16, or 8 beyond ~4700 streams), 16 / 8 = the round-2
+    engine with two / four streams per warp, 32 / 116 = the round-1 kernels (include/divans_b200.h)."""
 
-    def __init__(self, device=0, max_resident=0, lanes_per_stream=32):
+    def __init__(self, device=0, max_resident=0, lanes_per_stream=0):
         self._L = load_library()
         self._h = self._L.divans_b200_create(int(device), int(max_resident), int(lanes_per_stream))
         if not self._h:
@@ -220,6 +222,9 @@ class Engine:
     @property
     def launch_count(self):
         return int(self._L.divans_b200_launch_count(self._h))
+
+    def last_lanes(self):
+        return int(self._L.divans_b200_last_lanes(self._h))
 
     def last_kernel_ms(self):
         return float(self._L.divans_b200_last_kernel_ms(self._h))

@@ -46,6 +46,9 @@ __device__ __forceinline__ void st_u16(const void *p, uint32_t v) { asm volatile
 __device__ __forceinline__ void touch_l1(const void *p, const uint32_t smem_dummy) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dummy), "l"(p) : "memory");
 }
+// streaming accesses (touched once: payload words, decoded output): evict-first, so that they do not push the priors out of L2
+__device__ __forceinline__ uint32_t ld_stream_u32(const void *p) { uint32_t v; asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_stream_u64(const void *p, unsigned long long v) { asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ void st_u8(const void *p, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // tag bits of this lane's element(s): element i carries bit i of the 16-bit generation in its bit 15
@@ -208,10 +211,26 @@ struct FastK {
     uint32_t mytag;                                    // this lane's bit(s) of the stream's generation (lane_tag)
 };
 
-// One literal nibble after its symbol is known: exact start/freq, rANS step with eager refill, blend, store (+ tag).
-// `ev` / `mv`: the validated prior (elements of this lane, max); `st`: the rANS state that codes this nibble position.
+// One literal nibble after its symbol is known, in two parts.  (1) blend + store (+ tag) happens at once: the same prior may
+// be the next one to be loaded.  (2) exact start/freq and the rANS step with eager refill only have to be done before the state
+// is used again, one byte later: the loop runs the two steps of a byte back to back so that their (long, serial) dependency
+// chains overlap.  `ev` / `mv`: the validated prior (elements of this lane, max).
 template <int LPG>
-__device__ __forceinline__ void finish_v2(uint64_t &st, const uint32_t ev, const uint32_t mv, const int sym, const char *const p, const G2 g, FastK &f) {
+__device__ __forceinline__ void blend_store_v2(const uint32_t ev, const uint32_t mv, const int sym, const char *const p, const G2 g, const FastK &f) {
+    uint32_t c2;
+    if (LPG == 16) {
+        c2 = ev + ((g.l16 >= sym) ? (uint32_t)f.inc : 0u);
+        if ((int)mv + f.inc >= f.lim) { const uint32_t u = c2 + f.kp; c2 = u - (u >> 2); }   // frequentist_cdf.rs:79-84
+    } else {
+        const int d = sym - 2 * g.l16;                                       // elements >= sym take the increment
+        const uint32_t m = d <= 0 ? 0xffffffffu : (d == 1 ? 0xffff0000u : 0u);
+        c2 = ev + (f.incp & m);
+        if ((int)mv + f.inc >= f.lim) { const uint32_t u = c2 + f.kp; c2 = u - ((u >> 2) & 0x3fff3fffu); }
+    }
+    store_elems<LPG>(p, g.l16, c2 | f.mytag);
+}
+template <int LPG>
+__device__ __forceinline__ void rans_step_v2(uint64_t &st, const uint32_t ev, const uint32_t mv, const int sym, FastK &f) {
     const uint32_t inv = recip32(mv);
     uint32_t hi, lo;
     const int prev = (sym - 1) & 15;
@@ -231,20 +250,9 @@ __device__ __forceinline__ void finish_v2(uint64_t &st, const uint32_t ev, const
     if (x < (1ull << 31)) {                                                  // eager refill (dv_core.cuh literal_fast): same word order
         x = (x << 32) | (uint64_t)f.wnext;
         f.wi = min(f.wi + 1, f.wmax);
-        f.wnext = f.wbase[f.wi];                                             // consumed by the NEXT refill
+        f.wnext = ld_stream_u32(f.wbase + f.wi);                             // consumed by the NEXT refill
     }
     st = x;
-    uint32_t c2;
-    if (LPG == 16) {
-        c2 = ev + ((g.l16 >= sym) ? (uint32_t)f.inc : 0u);
-        if ((int)mv + f.inc >= f.lim) { const uint32_t u = c2 + f.kp; c2 = u - (u >> 2); }   // frequentist_cdf.rs:79-84
-    } else {
-        const int d = sym - 2 * g.l16;                                       // elements >= sym take the increment
-        const uint32_t m = d <= 0 ? 0xffffffffu : (d == 1 ? 0xffff0000u : 0u);
-        c2 = ev + (f.incp & m);
-        if ((int)mv + f.inc >= f.lim) { const uint32_t u = c2 + f.kp; c2 = u - ((u >> 2) & 0x3fff3fffu); }
-    }
-    store_elems<LPG>(p, g.l16, c2 | f.mytag);
 }
 
 // bin search: for a monotone CDF whose last element is max (> r) the number of elements with r < c[i] is 16 - sym
@@ -256,25 +264,169 @@ __device__ __forceinline__ int search_v2(const uint64_t st, const uint32_t ev, c
     return 16 - (__popc(__byte_perm(b0, b1, bsel)) >> 1);                    // bsel: PRMT selector [g, 4+g, g, 4+g]
 }
 
+// ---- dynamic context mixing >= 2 (codec/literal.rs:219-259), 16 lanes per stream: the stride prior `nb` (tagged literal table) is
+// mixed with the context-map prior `cm` (LIT_CM, untagged, defaulted eagerly), weights model_weights[high nibble ? 1 : 0] ----
+struct MixV { uint32_t c, maxv, cc, mc; };
+__device__ __forceinline__ MixV mixv_load(const char *nb, const char *cm, const int li) {
+    MixV v; v.c = ld_u16g(nb + 2 * li); v.maxv = ld_u16g(nb + 30); v.cc = ld_u16g(cm + 2 * li); v.mc = ld_u16g(cm + 30); return v;
+}
+struct MixS { int sym; uint32_t ca, ma; };
+__device__ __forceinline__ MixS mixv_search(const uint64_t st, const MixV v, const int norm, const uint32_t bsel) {
+    const uint32_t prod = v.mc * v.maxv;
+    int lz = prod == 0 ? 32 : __clz((int)prod); if (lz > 17) lz = 17;
+    const int shift = 17 - lz;
+    const uint32_t mixr = (uint32_t)norm, inv = (1u << 15) - mixr;
+    const uint32_t rs = (v.cc * v.maxv) >> shift, ro = (v.c * v.mc) >> shift;
+    MixS r;
+    r.ca = (uint32_t)(int)(short)((int)(rs * mixr + ro * inv + 1u) >> 15);   // frequentist_cdf.rs:58-72
+    r.ma = __shfl_sync(FULL, r.ca, 15, 16);
+    const uint32_t q = (((uint32_t)st & 0x7fffu) * r.ma) >> 15;
+    r.sym = 16 - __popc(__ballot_sync(FULL, q < r.ca) & bsel);
+    return r;
+}
+__device__ __forceinline__ void mixv_finish(uint64_t &st, const MixV v, const MixS ms, Weights &w, const char *nb, const char *cm, const G2 g, FastK &f,
+                                            const int cm_inc, const int cm_lim) {
+    const int sym = ms.sym, prev = (sym - 1) & 15;
+    const uint32_t cum_a = divq(ms.ca, recip32(ms.ma), ms.ma);
+    const uint32_t cum_pn = divq(v.cc, recip32(v.mc), v.mc) | (divq(v.c, recip32(v.maxv), v.maxv) << 16);
+    const uint32_t hi_a = __shfl_sync(FULL, cum_a, sym, 16), hi_pn = __shfl_sync(FULL, cum_pn, sym, 16);
+    uint32_t lo_a = __shfl_sync(FULL, cum_a, prev, 16), lo_pn = __shfl_sync(FULL, cum_pn, prev, 16);
+    if (sym == 0) { lo_a = 0; lo_pn = 0; }
+    const uint32_t freq = hi_a - lo_a - 1;
+    const int f_cm = (int)(short)((hi_pn & 0xffffu) - (lo_pn & 0xffffu) - 1);
+    const int f_nb = (int)(short)((hi_pn >> 16) - (lo_pn >> 16) - 1);
+    const uint32_t t = ((uint32_t)st & 0x7fffu) - lo_a - 1;
+    uint64_t x = (uint64_t)(freq & 0xffffu) * (st >> 15) + (uint64_t)t;   // ans.rs:230-244
+    if (x < (1ull << 31)) { x = (x << 32) | (uint64_t)f.wnext; f.wi = min(f.wi + 1, f.wmax); f.wnext = ld_stream_u32(f.wbase + f.wi); }
+    st = x;
+    weights_update32(w, f_cm, f_nb, (int)(short)freq);
+    uint32_t c2 = v.cc + ((g.l16 >= sym) ? (uint32_t)cm_inc : 0u);
+    if ((int)v.mc + cm_inc >= cm_lim) { const uint32_t u = c2 + f.kp; c2 = u - (u >> 2); }
+    st_u16(cm + 2 * g.l16, c2);
+    uint32_t s2 = v.c + ((g.l16 >= sym) ? (uint32_t)f.inc : 0u);
+    if ((int)v.maxv + f.inc >= f.lim) { const uint32_t u = s2 + f.kp; s2 = u - (u >> 2); }
+    st_u16(nb + 2 * g.l16, s2 | f.mytag);
+}
+// the mixing loop proper; same skeleton as the plain loop of literal_fast_v2 (which calls it)
+__device__ __forceinline__ void literal_mix_loop16(St &s, const G2 g, const bool active, uint32_t n) {
+    const int li = g.l16;
+    const int cfg = active ? s.lit_cfg : mm_cfg(4);
+    const uint32_t mm = (cfg & 0x100) ? 0xffu : 0u, o1 = (cfg & 0x200) ? 0xfu : 0u, fc = (cfg & 0x400) ? 0xfu : 0u;
+    const uint32_t sh = (uint32_t)(cfg >> 2) & 63u, which = (uint32_t)cfg & 3u;
+    const bool ro = (cfg & 0x800) != 0;                                      // mixing value 2: the stride prior is read, never adapted
+    FastK f;
+    f.inc = !active ? 0x10 : ro ? 0 : (int)(short)(s.ad_stride & 0xffff); f.lim = !active ? 0x2000 : ro ? 0x7fff : (s.ad_stride >> 16);
+    f.incp = 0; f.kp = (uint32_t)(li + 1);
+    f.mytag = lane_tag<16>(s.gen, li);
+    const int ch_inc = active ? (int)(short)(s.c->ad_cm_hi & 0xffff) : 0x10, ch_lim = active ? (s.c->ad_cm_hi >> 16) : 0x2000;
+    const int cl_inc = active ? (int)(short)(s.c->ad_cm_lo & 0xffff) : 0x10, cl_lim = active ? (s.c->ad_cm_lo >> 16) : 0x2000;
+    const uint32_t defe = default_elems<16>(li), bsel = 0xffffu << g.shift;
+    const unsigned gm = g.gmask;
+    const uint32_t slot_lo = (uint32_t)(uintptr_t)s.slot, slot_hi = (uint32_t)((uintptr_t)s.slot >> 32);
+    const uint32_t hi_tab = slot_lo + (uint32_t)OFF_LIT_HI + which * (65536u * 32u), lo_tab = slot_lo + (uint32_t)OFF_LIT_LO + which * (65536u * 32u);
+    const uint32_t cmb = slot_lo + (uint32_t)OFF_LIT_CM, t2 = slot_lo + (uint32_t)OFF_T2;
+    unsigned long long l8 = active ? s.l8 : 0ull;
+    uint32_t ctx = active ? s.lit_ctx : 0u;
+    uint32_t pcp = ld_u16g(mk_ptr(t2 + (uint32_t)(l8 >> 56) * 16u, slot_hi)) >> 8;
+    uint8_t *const dbase = s.out + s.out_pos;
+    uint32_t ap = (uint32_t)(uintptr_t)dbase & 7u;
+    const bool st_lane = g.store0 && active;
+    Coder k = s.cur;
+    if (!active) { k.p = reinterpret_cast<const uint32_t *>(s.slot + OFF_T2); k.left = 0; k.need_a = 0; k.need_b = 0; k.sym_count = 0; k.a = k.b = 1ull << 40; }
+    Weights wh = s.c->w_hi, wl = s.c->w_lo;
+    f.wbase = k.p; f.wmax = k.left + 1; f.wi = 0;
+    coder_fill(k);
+    f.wi = (uint32_t)(k.p - f.wbase);
+    if (k.need_b) { k.b = (k.b << 32) | (uint64_t)f.wbase[f.wi]; f.wi = min(f.wi + 1, f.wmax); k.need_b = 0; }
+    f.wnext = f.wbase[f.wi];
+    uint32_t done = 0;
+    while (done < n) {
+        uint32_t m = n - done;
+        if (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) {   // chunk restart, ans.rs:173-189
+            if (f.wi + 5 <= f.wmax) { k.a = (uint64_t)f.wbase[f.wi] | ((uint64_t)f.wbase[f.wi + 1] << 32); k.b = (uint64_t)f.wbase[f.wi + 2] | ((uint64_t)f.wbase[f.wi + 3] << 32); f.wi += 4; }
+            else { k.a = k.b = 0; f.wi = f.wmax; }
+            f.wnext = f.wbase[f.wi];
+            k.sym_count = 0;
+        }
+        m = min(m, (NUM_SYMBOLS_BEFORE_FLUSH - k.sym_count) >> 1);
+        m = min(m, __shfl_xor_sync(FULL, m, 16));
+        if (m == 0) break;
+        uint32_t ssb = (uint32_t)(l8 >> sh) & 0xffu;
+        const char *nbh = mk_ptr(hi_tab + (ctx * 256u + (ssb & mm & (~o1 & 0xffu))) * 32u, slot_hi), *cmh = mk_ptr(cmb + ctx * 32u, slot_hi);
+        __syncwarp();
+        MixV vh = mixv_load(nbh, cmh, li);
+        for (uint32_t i = 0; i < m; i++) {
+            // -- high nibble
+            const unsigned okh = __ballot_sync(FULL, !active || (vh.c & TAG_BITS16) == f.mytag);
+            if ((okh & gm) == gm) { vh.c &= 0x7fffu; vh.maxv &= 0x7fffu; } else { vh.c = defe; vh.maxv = 64u; }
+            const MixS sh_ = mixv_search(k.a, vh, wh.norm, bsel);
+            const uint32_t h = (uint32_t)sh_.sym;
+            const uint32_t ib = (mm & ssb) | ((~mm & 0xffu) & ctx), ic = (h & fc) | ((ctx & o1) << 4);
+            const char *const nbl = mk_ptr(lo_tab + (((ic >> 4) << 12) | (ib << 4) | (ic & 15u)) * 32u, slot_hi), *const cml = mk_ptr(cmb + (256u + h + 16u * ctx) * 32u, slot_hi);
+            __syncwarp();
+            MixV vl = mixv_load(nbl, cml, li);
+            mixv_finish(k.a, vh, sh_, wh, nbh, cmh, g, f, ch_inc, ch_lim);
+            // -- low nibble
+            const unsigned okl = __ballot_sync(FULL, !active || (vl.c & TAG_BITS16) == f.mytag);
+            if ((okl & gm) == gm) { vl.c &= 0x7fffu; vl.maxv &= 0x7fffu; } else { vl.c = defe; vl.maxv = 64u; }
+            const MixS sl_ = mixv_search(k.b, vl, wl.norm, bsel);
+            const uint32_t cur = ((uint32_t)sl_.sym | (h << 4)) & 0xffu;
+            l8 = (l8 >> 8) | ((unsigned long long)cur << 56);
+            if (st_lane && (ap & 7u) == 7u) st_stream_u64(dbase + (done + i) - 7, l8);
+            ap++;
+            const uint32_t cv = ld_u16g(mk_ptr(t2 + (cur * 8u + pcp) * 2u, slot_hi));
+            ctx = cv & 0xffu; pcp = cv >> 8;
+            ssb = (uint32_t)(l8 >> sh) & 0xffu;
+            nbh = mk_ptr(hi_tab + (ctx * 256u + (ssb & mm & (~o1 & 0xffu))) * 32u, slot_hi); cmh = mk_ptr(cmb + ctx * 32u, slot_hi);
+            __syncwarp();
+            vh = mixv_load(nbh, cmh, li);   // speculative on the last byte: inside the slot
+            mixv_finish(k.b, vl, sl_, wl, nbl, cml, g, f, cl_inc, cl_lim);
+        }
+        done += m;
+        if (active) k.sym_count += 2 * m;
+    }
+    if (!active) return;
+    if (g.store0) {
+        const uint32_t tail = min(ap & 7u, done);
+        for (uint32_t t = 0; t < tail; t++) dbase[done - tail + t] = (uint8_t)(l8 >> (8 * (8 - tail + t)));
+    }
+    if (f.wi >= f.wmax) { k.underflow = 1; f.wi = f.wmax - 1; }
+    k.p = f.wbase + f.wi; k.left = f.wmax - 1 - f.wi;
+    k.need_a = (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) ? 8u : 0u; k.need_b = 0;
+    s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += done; s.lit_left -= done;
+    s.c->w_hi = wh; s.c->w_lo = wl;
+}
+
 // Converged literal fast path: code_nibble_array (codec/literal.rs:261-394) for whole bytes of every stream of the warp.
 // `active`: this group really is at the start of a literal byte.  A group that has run out of streams rides along as a dummy
 // (it codes garbage against its own slot and stores no output) so that its warp-mates keep the fast loop.
 // PF: touch the 16 candidate priors of the next nibble as soon as everything but that nibble's predecessor is known -- the low
 // nibble's candidates (one per value of the high nibble) are 512 contiguous bytes (lit_index_lo), the high nibble's (one per
 // value of the low nibble just being decoded) go through T2 per candidate.
+// Returns false (nothing done) when some group cannot take the fast loop: dynamic context mixing, per-context mixing values, the
+// flat prior, wide speeds, untagged priors, or the first 7 bytes of a literal that began within 8 bytes of the ring start -- the
+// caller then codes one nibble per group through the generic core and the state machine.
 template <int LPG, bool PF>
-__device__ __forceinline__ void literal_fast_v2(St &s, Next &nx, const G2 g, const bool active, const uint32_t smem_dummy) {
+__device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, const bool active, const uint32_t smem_dummy) {
     uint32_t n = active ? s.lit_left : 0xffffffffu;
     if (LPG == 8) n = min(n, __shfl_xor_sync(FULL, n, 8));
     n = min(n, __shfl_xor_sync(FULL, n, 16));
-    // The first 7 bytes of a literal that began within 8 bytes of the ring start (also: of the stream) go through the generic
-    // core: until then last_8_literals is not a mirror of the output (cmd_to_raw/mod.rs:69-86) and cannot feed the 8-byte stores.
-    uint32_t qk = (active && s.c->lit_quirk && s.c->lit_total - s.lit_left < 7u) ? 7u - (s.c->lit_total - s.lit_left) : 0u;
-    if (LPG == 8) qk = max(qk, __shfl_xor_sync(FULL, qk, 8));
-    qk = max(qk, __shfl_xor_sync(FULL, qk, 16));
-    if (qk) n = min(n, qk);
-    // plain literals, one mixing value for the whole map (not the never-adapted flat prior), speeds that cannot wrap i16
-    if (qk == 0 && __all_sync(FULL, !active || (!s.mixing_trait && s.lit_cfg >= 0 && !(s.lit_cfg & 0x800) && s.speeds_small && s.tagged))) {
+    if (n < 12) return false;   // entering and leaving the loop costs about as much as a dozen nibbles of the generic path
+    // dynamic context mixing >= 2 with one mixing value for the whole map (16 lanes per stream): its own loop
+    if (LPG == 16 && __all_sync(FULL, !active || (s.mixing_trait && s.lit_cfg >= 0 && s.speeds_small && s.tagged &&
+                                                  !(s.c->lit_quirk && s.c->lit_total - s.lit_left < 7u)))) {
+        if (active && s.c->t2_dirty) { build_t2(g, s.slot, s.tables, s.pred_mode, s.btype_last); s.c->t2_dirty = false; }
+        __syncwarp();
+        literal_mix_loop16(s, g, active, n);
+        if (active) enter_lit_nibble<false, true, true>(s, nx);
+        return true;
+    }
+    // plain literals, one mixing value for the whole map (not the never-adapted flat prior), speeds that cannot wrap i16, tagged
+    // priors; and not the first 7 bytes of a literal that began within 8 bytes of the ring start (also: of the stream): until then
+    // last_8_literals is not a mirror of the output (cmd_to_raw/mod.rs:69-86) and cannot feed the 8-byte stores
+    if (!__all_sync(FULL, !active || (!s.mixing_trait && s.lit_cfg >= 0 && !(s.lit_cfg & 0x800) && s.speeds_small && s.tagged &&
+                                      !(s.c->lit_quirk && s.c->lit_total - s.lit_left < 7u)))) return false;
+    {
         if (active && s.c->t2_dirty) { build_t2(g, s.slot, s.tables, s.pred_mode, s.btype_last); s.c->t2_dirty = false; }
         __syncwarp();
         const int li = g.l16;
@@ -358,8 +510,8 @@ __device__ __forceinline__ void literal_fast_v2(St &s, Next &nx, const G2 g, con
                 const char *const pl = mk_ptr(lo_tab + idx_l * 32u, slot_hi);
                 __syncwarp();
                 const uint32_t el = load_elems<LPG>(pl, li), ml = ld_u16g(pl + 30);
-                // -- high nibble: finish
-                finish_v2<LPG>(k.a, eh_v, mh_v, h, ph, g, f);
+                // -- high nibble: blend (this prior may be the next one to be loaded)
+                blend_store_v2<LPG>(eh_v, mh_v, h, ph, g, f);
                 // -- low nibble: search
                 uint32_t el_v = el & ~tbits, ml_v = ml & 0x7fffu;
                 int l = search_v2<LPG>(k.b, el_v, ml_v, bsel);
@@ -370,7 +522,7 @@ __device__ __forceinline__ void literal_fast_v2(St &s, Next &nx, const G2 g, con
                 }
                 const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xffu;
                 l8 = (l8 >> 8) | ((unsigned long long)cur << 56);              // push_literal_byte, codec/interface.rs:280-284
-                if (st_lane && (ap & 7u) == 7u) *reinterpret_cast<unsigned long long *>(dbase + (done + i) - 7) = l8;
+                if (st_lane && (ap & 7u) == 7u) st_stream_u64(dbase + (done + i) - 7, l8);
                 ap++;
                 // -- context and priors of the next byte (get_prev_word_context, codec/literal.rs:87-117, through T2)
                 const uint32_t cv = ld_u16g(mk_ptr(t2 + (cur * 8u + pcp) * 2u, slot_hi));
@@ -385,13 +537,15 @@ __device__ __forceinline__ void literal_fast_v2(St &s, Next &nx, const G2 g, con
                     touch_l1(mk_ptr(lo_tab + row_l * 32u + (LPG == 16 ? li * 32u : li * 64u), slot_hi), smem_dummy);
                     if (LPG == 8) touch_l1(mk_ptr(lo_tab + row_l * 32u + li * 64u + 32u, slot_hi), smem_dummy);
                 }
-                // -- low nibble: finish
-                finish_v2<LPG>(k.b, el_v, ml_v, l, pl, g, f);
+                // -- low nibble: blend; then the rANS steps of both nibbles (state a before b: the order of the payload words)
+                blend_store_v2<LPG>(el_v, ml_v, l, pl, g, f);
+                rans_step_v2<LPG>(k.a, eh_v, mh_v, h, f);
+                rans_step_v2<LPG>(k.b, el_v, ml_v, l, f);
             }
             done += m;
             if (active) k.sym_count += 2 * m;
         }
-        if (!active) return;
+        if (!active) return true;
         // the bytes after the last aligned 8-byte store are still only in l8
         if (g.store0) {
             const uint32_t tail = min(ap & 7u, done);
@@ -403,25 +557,7 @@ __device__ __forceinline__ void literal_fast_v2(St &s, Next &nx, const G2 g, con
         k.need_a = (k.sym_count >= NUM_SYMBOLS_BEFORE_FLUSH) ? 8u : 0u; k.need_b = 0;
         s.cur = k; s.l8 = l8; s.lit_ctx = ctx; s.out_pos += done; s.lit_left -= done;
         enter_lit_nibble<false, true, true>(s, nx);
-        return;
-    }
-    // everything else (dynamic context mixing, per-context mixing values, the flat prior, wide speeds): the generic core
-    // (a dummy group codes against its slot's dummy CDF, like an idle group of the main loop)
-    for (uint32_t i = 0; i < n; i++) {
-        __syncwarp();
-        const int h = nibble_core_v2<LPG>(s, nx, g);
-        if (active) { s.lit_h = (uint32_t)h; enter_lit_nibble<false, false, true>(s, nx); }
-        __syncwarp();
-        const int l = nibble_core_v2<LPG>(s, nx, g);
-        if (active) {
-            const uint32_t cur = ((uint32_t)l | ((uint32_t)h << 4)) & 0xff;
-            s.l8 = (s.l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
-            if (g.store0) s.out[s.out_pos] = (uint8_t)cur;
-            s.out_pos++;
-            s.lit_left--;
-            lit_context(s);
-            enter_lit_nibble<false, true, true>(s, nx);
-        }
+        return true;
     }
 }
 

@@ -86,8 +86,7 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
         }
         // ---- whole literal bytes while every group is at a byte boundary of a literal (or out of work) ----
         const bool lit = s.state == S_LIT_HI;
-        if (__all_sync(FULL, lit || (exhausted && s.state == S_IDLE)) && __any_sync(FULL, lit)) {
-            literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy);
+        if (__all_sync(FULL, lit || (exhausted && s.state == S_IDLE)) && __any_sync(FULL, lit) && literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy)) {
             if (lit) {
                 if (s.cur.underflow) s.status = ST_NEED_INPUT;
                 if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); enter_cmd_type<false>(s, nx); }

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,6 +38,9 @@ struct divans_b200_ctx {
     cudaStream_t stream = nullptr;
     uint8_t *d_arena = nullptr; size_t arena_slots = 0;   // 16 MiB aligned view of d_arena_raw
     uint8_t *d_arena_raw = nullptr;
+    bool auto_lanes = false;         // lanes_per_stream 0: 16 lanes while the batch fits their residency, else 8 (twice the resident streams)
+    int last_lanes = 0;              // layout the most recent decode call used
+    uint32_t cap16 = 0, cap8 = 0;    // resident streams of the two v2 layouts
     bool prefetch = false;           // v2 engine: touch the candidate priors of the next nibble (env DIVANS_B200_PREFETCH, default off)
     int engine = 0;                  // 0: v2 (dv2_kernels.cu, lanes 16 or 8), 1: round-1 kernels (dv_kernels.cu, lanes 16 or 32)
     uint8_t *d_tables = nullptr;
@@ -101,6 +105,7 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
     // 16 (default, also 0): v2 engine, two streams per warp; 8: v2 engine, four streams per warp; 32: the round-1 kernel with one
     // warp per stream; 116: the round-1 16-lane kernel (kept for A/B measurements)
     ctx->engine = (lanes_per_stream == 32 || lanes_per_stream == 116) ? 1 : 0;
+    ctx->auto_lanes = lanes_per_stream == 0;
     ctx->lanes_per_stream = lanes_per_stream == 8 ? 8 : (lanes_per_stream == 32 ? 32 : 16);
     { const char *e = getenv("DIVANS_B200_PREFETCH"); ctx->prefetch = e && atoi(e) != 0; }
     cudaDeviceProp prop;
@@ -134,6 +139,15 @@ extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident
     if (auto_res > mem_cap) auto_res = mem_cap;
     ctx->max_resident = max_resident ? (max_resident < auto_res ? max_resident : auto_res) : auto_res;
     if (ctx->max_resident < groups_per_block) ctx->max_resident = groups_per_block;
+    if (ctx->engine == 0) {
+        auto cap = [&](int lanes) {
+            uint32_t c = (uint32_t)ctx->sm_count * (uint32_t)std::max(1, decode_max_blocks_per_sm_v2(lanes)) * (uint32_t)decode_groups_per_block_v2(lanes);
+            if (c > mem_cap) c = mem_cap;
+            if (max_resident && c > max_resident) c = max_resident;
+            return std::max(c, (uint32_t)decode_groups_per_block_v2(lanes));
+        };
+        ctx->cap16 = cap(16); ctx->cap8 = cap(8);
+    }
     return ctx;
 }
 
@@ -168,6 +182,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
 #define DV_KERNEL_VERSION "r2.3-v2-signtags"
 extern "C" const char *divans_b200_kernel_version(void) { return DV_KERNEL_VERSION; }
 extern "C" const char *divans_b200_last_error(divans_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int divans_b200_last_lanes(divans_b200_ctx *ctx) { return ctx ? ctx->last_lanes : 0; }
 extern "C" uint64_t divans_b200_launch_count(divans_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" float divans_b200_last_kernel_ms(divans_b200_ctx *ctx) {
     if (!ctx) return 0.f;
@@ -194,6 +209,7 @@ static DivansResult ensure_arena(divans_b200_ctx *ctx, size_t slots) {
     ctx->d_arena = reinterpret_cast<uint8_t *>(((uintptr_t)ctx->d_arena_raw + SLOT_STRIDE - 1) & ~(uintptr_t)(SLOT_STRIDE - 1));   // slots are 16 MiB aligned (dv_common.cuh)
     // the v2 engine reads literal priors it has never written (tag 0 = never valid) and keeps a header per slot: zero it all once
     CK(cudaMemset(ctx->d_arena, 0, slots * SLOT_STRIDE));
+    CK(cudaDeviceSynchronize());   // the memset runs on the legacy stream, the kernels on non-blocking ones: finish it before any launch
     ctx->arena_slots = slots;
     return DIVANS_SUCCESS;
 }
@@ -209,8 +225,16 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     if (ctx->busy_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
-    uint32_t gpb = ctx->groups_per_block;
-    uint32_t resident = (uint32_t)(n < ctx->max_resident ? n : ctx->max_resident);
+    int lanes = ctx->lanes_per_stream;
+    uint32_t gpb = ctx->groups_per_block, cap = ctx->max_resident;
+    if (ctx->engine == 0) {
+        // a batch that fits the 16-lane layout's residency runs there (fewer instructions per stream on the critical path of a
+        // half-empty GPU); a larger one takes 8 lanes per stream: twice the streams in flight instead of a second wave
+        if (ctx->auto_lanes) lanes = n <= ctx->cap16 ? 16 : 8;
+        gpb = (uint32_t)decode_groups_per_block_v2(lanes); cap = lanes == 16 ? ctx->cap16 : ctx->cap8;
+    }
+    ctx->last_lanes = lanes;
+    uint32_t resident = (uint32_t)(n < cap ? n : cap);
     uint32_t blocks = (resident + gpb - 1) / gpb;
     if (ensure_arena(ctx, (size_t)blocks * gpb) != DIVANS_SUCCESS) return DIVANS_FAILURE;
     if (!grow(ctx, &ctx->d_frame, &ctx->frame_cap, 4 * n)) return DIVANS_FAILURE;
@@ -230,7 +254,7 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     launch_frame(fp, ctx->d_payload, (uint64_t)ctx->payload_cap, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
-    if (!skip_decode) { if (ctx->engine == 0) launch_decode_v2(ctx->lanes_per_stream, ctx->prefetch, dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
+    if (!skip_decode) { if (ctx->engine == 0) launch_decode_v2(lanes, ctx->prefetch, dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;
@@ -274,23 +298,19 @@ extern "C" DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size
     CK(cudaMemcpyAsync(m + 2 * n, out_off, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(m + 3 * n, out_cap, n * 8, cudaMemcpyHostToDevice, st));
     int32_t *d_status = reinterpret_cast<int32_t *>(m + 5 * n);
+    CK(cudaMemsetAsync(ctx->d_out, 0, out_end, st));   // what the regions hold past out_len[i] is zeros, not an earlier batch
     DivansResult r = decode_device_nolock(ctx, n, ctx->d_in, m, m + n, ctx->d_out, m + 2 * n, m + 3 * n, m + 4 * n, d_status,
                                           in_sum > in_end ? in_sum : in_end, flags, st);
     if (r != DIVANS_SUCCESS) return r;
     CK(cudaMemcpyAsync(out_len, m + 4 * n, n * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // Copy back only what was produced, and never outside a declared region out[out_off[i] .. +out_cap[i]): consecutive
-    // streams whose regions are exactly adjacent AND completely filled share one transfer; the run ends with the first
-    // stream that left room in its region.
-    size_t i = 0;
-    while (i < n) {
-        const uint64_t lo = out_off[i];
-        uint64_t hi = lo + (out_len[i] < out_cap[i] ? out_len[i] : out_cap[i]);
+    // Copy back whole regions (zeros past out_len[i]: d_out was cleared before the kernels) and never a byte outside a declared
+    // region out[out_off[i] .. +out_cap[i]): consecutive streams whose regions are exactly adjacent share one transfer.
+    for (size_t i = 0; i < n;) {
+        const uint64_t lo = out_off[i]; uint64_t hi = lo + out_cap[i];
         size_t j = i + 1;
-        while (j < n && out_len[j - 1] >= out_cap[j - 1] && out_off[j] == out_off[j - 1] + out_cap[j - 1]) {
-            hi = out_off[j] + (out_len[j] < out_cap[j] ? out_len[j] : out_cap[j]); j++;
-        }
+        while (j < n && out_off[j] == hi) { hi += out_cap[j]; j++; }
         if (hi > lo) CK(cudaMemcpyAsync(out + lo, ctx->d_out + lo, hi - lo, cudaMemcpyDeviceToHost, st));
         i = j;
     }
@@ -589,7 +609,7 @@ static divans_b200_ctx *shared_ctx() {
         int dev = 0;
         const char *e = getenv("DIVANS_B200_DEVICE");
         if (e) dev = atoi(e);
-        g_shared_ctx = divans_b200_create(dev, 0, 32);
+        g_shared_ctx = divans_b200_create(dev, 0, 0);
     }
     return g_shared_ctx;
 }

@@ -216,15 +216,15 @@ template <bool ENC> __device__ __forceinline__ void enter_bt_mnemonic(St &s, Nex
     }
     set_next<ENC>(nx, A_misc(s, MI_BTYPE + BT_MNEMONIC + which), SPK_SLOW, varint);
 }
-template <bool ENC> __device__ __forceinline__ void bt_done(St &s, Next &nx, uint32_t bt) {
+// returns true when the block switch is complete (the caller's common tail fetches the next command)
+template <bool ENC> __device__ __forceinline__ bool bt_done(St &s, Next &nx, uint32_t bt) {
     if (s.f0 == 0) {
         s.f1 = bt; s.state = S_BT_STRIDE;
         set_next<ENC>(nx, A_misc(s, MI_BTYPE + BT_STRIDE), SPK_SLOW, (int)(s.c->desired_force_stride == 9 ? (s.c->e1 & 0xf) : s.c->desired_force_stride));
-    } else {
-        obs_btype(s, (int)s.f0, bt);
-        if (ENC) s.c->in.pos++;
-        enter_cmd_type<ENC>(s, nx);
+        return false;
     }
+    obs_btype(s, (int)s.f0, bt);
+    return true;
 }
 template <bool ENC> __device__ __forceinline__ const uint8_t *pm_rec(const St &s) { return s.c->in.pms + (size_t)s.c->e0 * (32 + 16384 + 1024 + 8192); }
 template <bool ENC> __device__ __forceinline__ void enter_pm_speed(St &s, Next &nx) {
@@ -278,6 +278,9 @@ template <bool ENC> __device__ __forceinline__ void pm_map_store(St &s, Next &nx
 // The transition: consume the nibble just coded in state s.state, perform its side effects, choose the next prior.
 template <bool ENC, bool V2 = false>
 __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib) {
+    // Two tails are shared by all states (one copy of their code keeps the kernel inside the instruction cache when the
+    // streams of a batch are in different states): 1 = the command is complete, fetch the next one; 2 = a literal of tail_len bytes begins.
+    int tail = 0; uint32_t tail_len = 0;
     // ---- hot: literal nibbles ----
     if (s.state == S_LIT_HI) { s.lit_h = (uint32_t)nib; enter_lit_nibble<ENC, false, V2>(s, nx); return; }
     if (s.state == S_LIT_LO) {
@@ -285,13 +288,10 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         s.l8 = (s.l8 >> 8) | ((unsigned long long)cur << 56);   // push_literal_byte, codec/interface.rs:280-284
         if (g.store0) s.out[s.out_pos] = (uint8_t)cur;
         s.out_pos++;
-        if (--s.lit_left == 0) {
-            swap_coders(s);
-            if (ENC) s.c->in.pos++;
-            enter_cmd_type<ENC>(s, nx);
-        } else { lit_context(s); enter_lit_nibble<ENC, true, V2>(s, nx); }
-        return;
-    }
+        if (--s.lit_left != 0) { lit_context(s); enter_lit_nibble<ENC, true, V2>(s, nx); return; }
+        swap_coders(s);
+        tail = 1;
+    } else
     switch (s.state) {
     case S_CMD_TYPE: {
         if (nib == 0xf) { s.state = S_IDLE; return; }   // end of stream (trailer/CRC: frame kernel); the main loop parks the group
@@ -332,20 +332,20 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             uint32_t lllen = bitlen32(s.c->e1 - 15u);
             set_next<ENC>(nx, ctype_slab(s, g, BL(s, 1, 0)) + CT_LL_SIZE_BEG * 16, SPK_MUD, (int)(lllen < 15 ? lllen : 15));
         } else if (nib == 15) { s.f3 = 1; enter_ll_count_small<ENC>(s, nx, g); }
-        else { uint32_t len = (uint32_t)nib + 1; s.c->last_llen = len; start_literal<ENC, V2>(s, nx, g, len); }
+        else { tail_len = (uint32_t)nib + 1; s.c->last_llen = tail_len; tail = 2; }
     } break;
     case S_LL_SIZE_BEG: {
         if (nib == 15) {
             s.state = S_LL_SIZE_LAST;
             set_next<ENC>(nx, ctype_slab(s, g, BL(s, 1, 0)) + CT_LL_SIZE_LAST * 16, SPK_MUD, (int)((bitlen32(s.c->e1 - 15u) - 15u) & 0xf));
-        } else if (nib <= 1) start_literal<ENC, V2>(s, nx, g, 15u + (uint32_t)nib);   // last_llen NOT updated (literal.rs:608-616)
+        } else if (nib <= 1) { tail_len = 15u + (uint32_t)nib; tail = 2; }   // last_llen NOT updated (literal.rs:608-616)
         else { s.f0 = round_up_mod_4((uint32_t)nib - 1); s.f1 = 1u << (nib - 1); enter_ll_mant<ENC>(s, nx, g); }
     } break;
     case S_LL_SIZE_LAST: { s.f0 = round_up_mod_4((uint32_t)nib + 14); s.f1 = 1u << (nib + 14); enter_ll_mant<ENC>(s, nx, g); } break;
     case S_LL_MANT: {
         uint32_t next_rem = s.f0 - 4;
         s.f1 |= (uint32_t)nib << next_rem;
-        if (next_rem == 0) { uint32_t len = s.f1 + 15u; s.c->last_llen = len; start_literal<ENC, V2>(s, nx, g, len); }
+        if (next_rem == 0) { tail_len = s.f1 + 15u; s.c->last_llen = tail_len; tail = 2; }
         else { s.f0 = next_rem; enter_ll_mant<ENC>(s, nx, g); }
     } break;
     // ---- copy ----
@@ -404,8 +404,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             if ((uint64_t)len > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
             replay_copy(g, s.out, s.out_pos, dist, len);
             s.out_pos += len;
-            if (ENC) s.c->in.pos++;
-            enter_cmd_type<ENC>(s, nx);
+            tail = 1;
         }
     } break;
     // ---- dict ----
@@ -436,20 +435,19 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         for (int i = g.l16; i < n; i += g.nl) s.out[s.out_pos + i] = scratch[i];
         __syncwarp(g.gmask);
         s.out_pos += (uint32_t)n;
-        if (ENC) s.c->in.pos++;
-        enter_cmd_type<ENC>(s, nx);
+        tail = 1;
     } break;
     // ---- block switches ----
     case S_BT_MNEMONIC: {
         int which = (int)s.f0;
-        if (nib == 0) bt_done<ENC>(s, nx, BL(s, which, 1));
-        else if (nib == 1) bt_done<ENC>(s, nx, (BMAX(s, which) + 1) & 0xff);
-        else if (nib != 15) bt_done<ENC>(s, nx, (uint32_t)nib - 2);
+        if (nib == 0) tail = bt_done<ENC>(s, nx, BL(s, which, 1)) ? 1 : 0;
+        else if (nib == 1) tail = bt_done<ENC>(s, nx, (BMAX(s, which) + 1) & 0xff) ? 1 : 0;
+        else if (nib != 15) tail = bt_done<ENC>(s, nx, (uint32_t)nib - 2) ? 1 : 0;
         else { s.state = S_BT_FIRST; set_next<ENC>(nx, A_misc(s, MI_BTYPE + BT_FIRST + which), SPK_SLOW, (int)(s.c->e0 & 0xf)); }
     } break;
     case S_BT_FIRST: { s.f1 = (uint32_t)nib; s.state = S_BT_SECOND; set_next<ENC>(nx, A_misc(s, MI_BTYPE + BT_SECOND + (int)s.f0), SPK_SLOW, (int)((s.c->e0 >> 4) & 0xf)); } break;
-    case S_BT_SECOND: bt_done<ENC>(s, nx, ((uint32_t)nib << 4) | s.f1); break;
-    case S_BT_STRIDE: { obs_btype(s, 0, s.f1); s.btype_last = s.f1; s.c->t2_dirty = true; if (ENC) s.c->in.pos++; enter_cmd_type<ENC>(s, nx); } break;
+    case S_BT_SECOND: tail = bt_done<ENC>(s, nx, ((uint32_t)nib << 4) | s.f1) ? 1 : 0; break;
+    case S_BT_STRIDE: { obs_btype(s, 0, s.f1); s.btype_last = s.f1; s.c->t2_dirty = true; tail = 1; } break;
     // ---- prediction mode ----
     case S_PM_MODE: {
         s.f0 = (uint32_t)nib; s.state = S_PM_MIX;
@@ -502,12 +500,13 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             if (V2 && !s.speeds_small && s.tagged) { v2_make_untagged(g, s.slot, s.c->bitmaps, s.gen); s.tagged = false; }
             if (!V2 && !s.speeds_small && g.store0) reinterpret_cast<uint32_t *>(s.slot + OFF_HDR)[1] = 1u;   // elements may use their sign bits: the v2 engine must wipe before trusting tags
             s.c->lit_slabs_ready = false; s.c->t2_dirty = true; s.c->pm_seen = true;
-            if (ENC) s.c->in.pos++;
-            enter_cmd_type<ENC>(s, nx);
+            tail = 1;
         } else enter_pm_mixval<ENC>(s, nx);
     } break;
     default: s.status = ST_FAIL; break;
     }
+    if (tail == 1) { if (ENC) s.c->in.pos++; enter_cmd_type<ENC>(s, nx); }
+    else if (tail == 2) start_literal<ENC, V2>(s, nx, g, tail_len);
 }
 
 // fresh book-keeping for a new stream (CrossCommandBookKeeping::new codec/interface.rs:348-402, LiteralBookKeeping::new :246-264)

@@ -114,15 +114,17 @@ typedef struct divans_b200_ctx divans_b200_ctx;
 /* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
 
 /* device = CUDA ordinal; max_resident = cap on concurrently resident streams (0 = auto: sized to the GPU);
- * lanes_per_stream = 16 (default, also for 0: two streams per warp, one CDF element per lane), 8 (four streams per warp,
- * two elements per lane: twice the resident streams, for batches beyond ~4700 streams) -- both the round-2 engine -- or
- * 32 (round-1 kernel, one warp owns one stream, the upper half-warp mirrors the lower); 116 selects the round-1 16-lane
- * kernel (A/B measurements). */
+ * lanes_per_stream: 0 = by batch size (16 lanes per stream while the batch fits their residency, 8 beyond it); 16 = two
+ * streams per warp, one CDF element per lane; 8 = four streams per warp, two elements per lane (twice the resident streams) --
+ * all three the round-2 engine; 32 = round-1 kernel, one warp owns one stream (the upper half-warp mirrors the lower);
+ * 116 = the round-1 16-lane kernel (A/B measurements). */
 divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream);
 void divans_b200_destroy(divans_b200_ctx *ctx);
 const char *divans_b200_last_error(divans_b200_ctx *ctx);
 /* version string of the decode kernels in this build (quoted next to profile-derived numbers) */
 const char *divans_b200_kernel_version(void);
+/* lanes per stream the most recent decode call of this context ran with */
+int divans_b200_last_lanes(divans_b200_ctx *ctx);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches claim) */
 uint64_t divans_b200_launch_count(divans_b200_ctx *ctx);
 /* device time of the most recent decode/encode kernel(s) in milliseconds (CUDA events on the context stream) */
@@ -131,8 +133,8 @@ float divans_b200_last_kernel_ms(divans_b200_ctx *ctx);
 float divans_b200_last_main_kernel_ms(divans_b200_ctx *ctx);
 
 /* Decode n independent, complete .divans streams held in HOST memory.
- * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]) and only
- * out[out_off[i] .. +out_len[i]) is written.  Input regions may alias.
+ * stream i = in[in_off[i] .. in_off[i]+in_len[i]); its output goes to out[out_off[i] .. +out_cap[i]); the region is written
+ * whole (zeros past out_len[i]), nothing outside the regions is touched.  Input regions may alias.
  * Includes H2D of the inputs and D2H of outputs inside the call.  Returns DIVANS_SUCCESS if the batch ran
  * (inspect status[] per stream), DIVANS_FAILURE on CUDA/context errors. */
 DivansResult divans_b200_decode_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *in, const uint64_t *in_off,

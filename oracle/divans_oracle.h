@@ -5,12 +5,14 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
  * (divans_b200/, include/) never includes, links or calls anything in oracle/.
  *
- * Parity status: the reference is a Rust crate and no Rust toolchain exists in the build
- * container, so this restatement cannot be diffed against the real binary ("parity unpinned"
- * for whole compressed streams -- the reference holds no golden .divans vectors either).
- * It IS pinned against every known-answer test the reference carries for this path
- * (CRC32C, mux framing vector, dictionary words, fast divide, f8 speed codec, IR->raw
- * fixtures, ratio ceilings); see tests/test_oracle_kat.py.
+ * Parity status: the reference is a Rust crate and no Rust toolchain exists in the build container, so this restatement cannot be
+ * diffed against the real binary.  It IS pinned at whole-bitstream level by the one compressed stream the reference tree holds
+ * (wasm/wasm.html:98-107, tests/golden/ref_wasm_example.divans): under model revision DVO_MODEL_WASM_2018 (below) the decoder
+ * turns its 113 bytes into a CRC-valid English text and the encoder reproduces the 113 bytes byte for byte; the revision
+ * differs from the mounted source in three named constructs of the PredictionMode / copy command coding, which are therefore
+ * "parity unpinned" under DVO_MODEL_CURRENT (as are context-map value coding and dynamic context mixing >= 2, which the stream
+ * does not use).  It is also pinned against every known-answer test the reference carries for this path (CRC32C, mux framing
+ * vector, dictionary words, fast divide, f8 speed codec, IR->raw fixtures, ratio ceilings); see tests/test_oracle_kat.py.
  *
  * Every function cites the reference file:line it restates (paths relative to the
  * reference tree, dropbox/divans @ 23459c22).
