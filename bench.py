@@ -317,7 +317,7 @@ def run_entropy(args, eng, rank, world, dev):
                           "warmup": 2, "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/u64",
                           "data": "synthetic",
                           "config": {"workload": "entropy sweep (BASELINE configs[4]): %d x 1 MiB Bernoulli-bit streams per GPU, p in {0.5, 0.9, 0.99}, "
-                                                 "literal-only encoding" % n, "lanes_per_stream": args.lanes}, "sweep": res}))
+                                                 "literal-only encoding" % n, "lanes_per_stream": eng.last_lanes()}, "sweep": res}))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -357,9 +357,7 @@ def main():
 
     if not args.streams:
         args.streams = STREAMS_PER_GPU if world == 1 else STREAMS_PER_GPU_SCALING
-    if not args.lanes:
-        args.lanes = 16 if args.streams <= 4736 else 8      # 8 lanes per stream keep twice as many streams resident
-    eng = divans_b200.Engine(local_rank, 0, args.lanes)
+    eng = divans_b200.Engine(local_rank, 0, args.lanes)   # 0: the library picks 16 lanes per stream while the batch is resident, else 8
     if args.workload == "entropy":
         return run_entropy(args, eng, rank, world, dev)
     n = args.streams
@@ -394,6 +392,7 @@ def main():
     barrier()
     assert bool((d_status == 0).all()) and bool((d_out_len == STREAM_BYTES).all()), "decode failed"
     assert bool((d_out[:out_bytes].cpu().numpy() == blob).all()), "GPU output differs from the original input"
+    args.lanes = eng.last_lanes()                    # the layout the library used for this batch size
     launches0 = eng.launch_count
     try:
         dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)

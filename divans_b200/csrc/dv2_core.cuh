@@ -492,7 +492,7 @@ __device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, con
                 uint32_t eh_v = eh & ~tbits, mh_v = mh & 0x7fffu;
                 int h = search_v2<LPG>(k.a, eh_v, mh_v, bsel);
                 const unsigned okh = __ballot_sync(FULL, !active || (eh & tbits) == f.mytag);
-                if (okh != FULL) {                                            // some group met a prior of an older stream: default CDF
+                if (__builtin_expect(okh != FULL, 0)) {                       // some group met a prior of an older stream: default CDF
                     if ((okh & gm) != gm) { eh_v = defe; mh_v = 64u; }
                     h = search_v2<LPG>(k.a, eh_v, mh_v, bsel);
                 }
@@ -516,7 +516,7 @@ __device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, con
                 uint32_t el_v = el & ~tbits, ml_v = ml & 0x7fffu;
                 int l = search_v2<LPG>(k.b, el_v, ml_v, bsel);
                 const unsigned okl = __ballot_sync(FULL, !active || (el & tbits) == f.mytag);
-                if (okl != FULL) {
+                if (__builtin_expect(okl != FULL, 0)) {
                     if ((okl & gm) != gm) { el_v = defe; ml_v = 64u; }
                     l = search_v2<LPG>(k.b, el_v, ml_v, bsel);
                 }

@@ -6,10 +6,10 @@
 namespace dv {
 
 constexpr int DEC2_BLOCK_THREADS = 32;          // one warp per block: blocks spread evenly over the SMs
-constexpr int DEC2_MIN_BLOCKS = 16;             // 16 warps per SM, <= 128 registers
+constexpr int DEC2_MAX_REGS = 144;              // 14 one-warp blocks per SM: 4096 streams of 16 lanes (8192 of 8) are resident on 148 SMs
 
 template <int LPG, bool PF>
-__global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_kernel_v2(DecodeParams p) {
+__global__ void __maxnreg__(DEC2_MAX_REGS) decode_kernel_v2(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     // one dummy word per lane behind the groups' cold state: destination of the L1-touching async copies (dv2_core.cuh)
     const uint32_t smem_dummy = (uint32_t)__cvta_generic_to_shared(smem + (DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2) + 4u * threadIdx.x;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
         if (__all_sync(FULL, lit || (exhausted && s.state == S_IDLE)) && __any_sync(FULL, lit) && literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy)) {
             if (lit) {
                 if (s.cur.underflow) s.status = ST_NEED_INPUT;
-                if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); enter_cmd_type<false>(s, nx); }
+                if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); enter_cmd_type<false>(s, nx); }
                 if (s.status != ST_OK) {
                     if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
                     s.state = S_IDLE; s.status = ST_OK;

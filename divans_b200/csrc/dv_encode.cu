@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
         }
         if (__all_sync(FULL, s.state == S_LIT_HI)) {
             literal_fast<true, LPS>(s, nx, g, writer);
-            if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); s.c->in.pos++; enter_cmd_type<true>(s, nx); }
+            if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); s.c->in.pos++; enter_cmd_type<true>(s, nx); }
             continue;
         }
         const bool busy = s.state != S_IDLE;

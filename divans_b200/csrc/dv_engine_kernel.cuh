@@ -106,7 +106,16 @@ __device__ __forceinline__ unsigned long long reseed_last8(const St &s) {
     }
     return v;
 }
-__device__ __forceinline__ void swap_coders(St &s) { Coder t = s.cur; s.cur = s.c->oth; s.c->oth = t; s.c->cur_is_lit = !s.c->cur_is_lit; }
+// The parked coder lives in the group's shared-memory state.  Every lane reads it, ONE lane writes the coder being parked (all
+// lanes hold identical copies), with the group synchronised on both sides: single writer, no read of a half-written struct.
+__device__ __forceinline__ void swap_coders(St &s, const G2 g) {
+    const Coder parked = s.c->oth;
+    const bool was_lit = s.c->cur_is_lit;
+    __syncwarp(g.gmask);
+    if (g.store0) { s.c->oth = s.cur; s.c->cur_is_lit = !was_lit; }
+    __syncwarp(g.gmask);
+    s.cur = parked;
+}
 
 template <bool ENC, bool V2 = false>
 __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint32_t len) {
@@ -119,7 +128,7 @@ __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint3
     }
     s.l8 = reseed_last8(s);
     s.c->lit_quirk = (s.out_pos & (s.c->ring_len - 1)) < 8u; s.c->lit_total = len;
-    swap_coders(s);
+    swap_coders(s, g);
     s.lit_left = len;
     if (ENC) {
         s.c->e1 = len;
@@ -289,7 +298,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         if (g.store0) s.out[s.out_pos] = (uint8_t)cur;
         s.out_pos++;
         if (--s.lit_left != 0) { lit_context(s); enter_lit_nibble<ENC, true, V2>(s, nx); return; }
-        swap_coders(s);
+        swap_coders(s, g);
         tail = 1;
     } else
     switch (s.state) {

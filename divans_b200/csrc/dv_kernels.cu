@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
         if (__all_sync(FULL, s.state == S_LIT_HI)) {
             literal_fast<false, LPS>(s, nx, g, writer);
             if (s.cur.underflow) s.status = ST_NEED_INPUT;
-            if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s); enter_cmd_type<false>(s, nx); }
+            if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); enter_cmd_type<false>(s, nx); }
             if (s.status != ST_OK) {
                 if (g.store0) { p.out_len[s.c->sidx] = s.out_pos; p.status[s.c->sidx] = s.status; }
                 s.state = S_IDLE; s.status = ST_OK;
