@@ -3,16 +3,18 @@
 // the same command state machine (dv_engine_kernel.cuh, transition<false, true>) as the round-1 decoders.
 #include "dv2_core.cuh"
 
+#include <algorithm>
 namespace dv {
 
 constexpr int DEC2_BLOCK_THREADS = 32;          // one warp per block: blocks spread evenly over the SMs
-constexpr int DEC2_MAX_REGS = 144;              // 14 one-warp blocks per SM: 4096 streams of 16 lanes (8192 of 8) are resident on 148 SMs
+constexpr int DEC2_MIN_BLOCKS = 16;             // 4 one-warp blocks per scheduler partition (16 K registers each): <= 128 registers.  (144 registers = 3 per
+                                                // partition = 12 per SM: 3552 resident 16-lane streams, measured 66 ms for 4096 -- a second wave)
 
 template <int LPG, bool PF>
-__global__ void __maxnreg__(DEC2_MAX_REGS) decode_kernel_v2(DecodeParams p) {
+__global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_kernel_v2(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     // one dummy word per lane behind the groups' cold state: destination of the L1-touching async copies (dv2_core.cuh)
-    const uint32_t smem_dummy = (uint32_t)__cvta_generic_to_shared(smem + (DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2) + 4u * threadIdx.x;
+    const uint32_t smem_dummy = PF ? (uint32_t)__cvta_generic_to_shared(smem + (DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2) + 4u * threadIdx.x : 0u;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     constexpr int GPW = 32 / LPG;
@@ -118,13 +120,14 @@ __global__ void __maxnreg__(DEC2_MAX_REGS) decode_kernel_v2(DecodeParams p) {
     if (g.store0) *reinterpret_cast<uint32_t *>(s.slot + OFF_HDR) = s.c->gen_ctr;
 }
 
-template <int LPG> static size_t smem_v2() { return (size_t)(DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2 + 4 * DEC2_BLOCK_THREADS; }
+// per block: the groups' cold state (+ one dummy word per thread, the target of the candidate-touch prefetch, when that is compiled in)
+template <int LPG, bool PF> static size_t smem_v2() { return (size_t)(DEC2_BLOCK_THREADS / LPG) * SMEM_BYTES_PER_GROUP_V2 + (PF ? 4 * DEC2_BLOCK_THREADS : 0); }
 template <int LPG, bool PF> static void launch_v2(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
-    decode_kernel_v2<LPG, PF><<<n_blocks, DEC2_BLOCK_THREADS, smem_v2<LPG>(), st>>>(p);
+    decode_kernel_v2<LPG, PF><<<n_blocks, DEC2_BLOCK_THREADS, smem_v2<LPG, PF>(), st>>>(p);
 }
+template <int LPG, bool PF> static int tune_v2() { return stream_kernel_blocks_per_sm(decode_kernel_v2<LPG, PF>, DEC2_BLOCK_THREADS, smem_v2<LPG, PF>()); }
 template <int LPG> static int max_blocks_v2() {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel_v2<LPG, false>, DEC2_BLOCK_THREADS, smem_v2<LPG>());
+    const int nb = std::min(tune_v2<LPG, false>(), tune_v2<LPG, true>());
     return nb;
 }
 void launch_decode_v2(int lanes_per_stream, bool prefetch, const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {

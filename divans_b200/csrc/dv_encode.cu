@@ -383,8 +383,7 @@ void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st) {
     encode_mux_kernel<<<(p.n_streams + 3) / 4, 128, 0, st>>>(p);
 }
 int encode_max_blocks_per_sm() {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_model_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
+    const int nb = stream_kernel_blocks_per_sm(encode_model_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
 

@@ -105,7 +105,7 @@ struct Cold {
     bool desired_do_context_map, have_desired_adapt;
     int desired_adapt0, desired_adapt1, desired_adapt2, desired_adapt3;
     // lazily-initialised prior slabs: [0..47] literal, [48..55] ctype, [56..63] dprior, [64] flags; then dictionary scratch
-    uint32_t bitmaps[80];
+    uint32_t bitmaps[66];
     uint8_t scratch[64];
 };
 

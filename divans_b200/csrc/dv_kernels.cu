@@ -258,8 +258,7 @@ void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) 
     decode_kernel<32><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
 }
 int decode_max_blocks_per_sm32() {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<32>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_BYTES_PER_GROUP);
+    const int nb = stream_kernel_blocks_per_sm(decode_kernel<32>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
 #else
@@ -268,8 +267,7 @@ void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) 
     decode_kernel<16><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
 }
 int decode_max_blocks_per_sm16() {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
+    const int nb = stream_kernel_blocks_per_sm(decode_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
 #endif
