@@ -24,6 +24,8 @@ FLAG_SKIP_CRC = 1
 FLAG_NO_CRC_KERNEL = 2
 FLAG_MODEL_WASM_2018 = 4   # include/divans_b200.h: the model revision of the reference-held stream wasm/wasm.html:98-107
 MODEL_CURRENT, MODEL_WASM_2018 = 0, 1
+FLAG_CDF_BLEND = 8         # include/divans_b200.h: streams coded with the reference's feature="blend" probability model
+CDF_FREQUENTIST, CDF_BLEND = 0, 1
 
 # symbols include/divans_b200.h declares (checked by the CPU test-suite)
 REFERENCE_FFI_SYMBOLS = [
@@ -52,7 +54,7 @@ class EncodeOptions(ctypes.Structure):
         ("window_size", ctypes.c_int32), ("dynamic_context_mixing", ctypes.c_int32), ("prior_depth", ctypes.c_int32),
         ("use_context_map", ctypes.c_int32), ("force_stride", ctypes.c_int32), ("have_literal_adaptation", ctypes.c_int32),
         ("literal_adaptation", (ctypes.c_int16 * 2) * 4), ("literal_pred_mode", ctypes.c_int32),
-        ("literal_mixing_value", ctypes.c_int32), ("model_rev", ctypes.c_int32),
+        ("literal_mixing_value", ctypes.c_int32), ("model_rev", ctypes.c_int32), ("cdf_model", ctypes.c_int32),
     ]
 
 

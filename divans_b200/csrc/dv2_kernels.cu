@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
     g.gmask = (LPG == 16 ? 0xffffu : 0xffu) << g.shift;
     g.store0 = g.l16 == 0;
     g.nl = LPG;
+    g.grp = group_in_block;
+    g.blend = false;
 
     St s;
     s.slot = p.arena + (uint64_t)slot * SLOT_STRIDE;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
                     uint64_t cap = p.out_cap[v];
                     s.c->out_cap = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap; s.out_pos = 0;
                     s.c->ring_len = 1u << in[5];
-                    reset_slot_v2(g, s.slot, s.c->bitmaps);
+                    reset_slot_v2(g, s.slot);
                     st_reset(s);
                     // a new generation: every literal prior of the slot reads as the default CDF until this stream writes it.  The
                     // tables are wiped when the 16-bit generation wraps, or when an earlier user of the slot (a stream with

@@ -179,7 +179,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     delete ctx;
 }
 // bumped whenever a decode kernel changes: profiles/traffic.json (an ncu capture) is only quoted by bench.py for the version it measured
-#define DV_KERNEL_VERSION "r2.5-v2-signtags"
+#define DV_KERNEL_VERSION "r2.6-v2-signtags"
 extern "C" const char *divans_b200_kernel_version(void) { return DV_KERNEL_VERSION; }
 extern "C" const char *divans_b200_last_error(divans_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int divans_b200_last_lanes(divans_b200_ctx *ctx) { return ctx ? ctx->last_lanes : 0; }
@@ -227,7 +227,12 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     if (ctx->busy_recorded) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
     int lanes = ctx->lanes_per_stream;
     uint32_t gpb = ctx->groups_per_block, cap = ctx->max_resident;
-    if (ctx->engine == 0) {
+    const bool blend = (flags & DIVANS_B200_FLAG_CDF_BLEND) != 0;   // BlendCDF16 streams: the round-1 engine's generic path, 16 lanes
+    if (blend) {
+        lanes = 16; gpb = (uint32_t)(DECODE_BLOCK_THREADS / 16);
+        cap = (uint32_t)ctx->sm_count * (uint32_t)std::max(1, decode_max_blocks_per_sm16_blend()) * gpb;
+        if (cap > ctx->max_resident) cap = std::max(ctx->max_resident / gpb * gpb, gpb);   // (memory / caller limits of the context)
+    } else if (ctx->engine == 0) {
         // a batch that fits the 16-lane layout's residency runs there (fewer instructions per stream on the critical path of a
         // half-empty GPU); a larger one takes 8 lanes per stream: twice the streams in flight instead of a second wave
         if (ctx->auto_lanes) lanes = n <= ctx->cap16 ? 16 : 8;
@@ -254,7 +259,7 @@ static DivansResult decode_device_nolock(divans_b200_ctx *ctx, size_t n, const u
     launch_frame(fp, ctx->d_payload, (uint64_t)ctx->payload_cap, st);
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: frame kernel ok (n=%zu)\n", n); }
     CK(cudaEventRecord(ctx->evm, st));
-    if (!skip_decode) { if (ctx->engine == 0) launch_decode_v2(lanes, ctx->prefetch, dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
+    if (!skip_decode) { if (blend) launch_decode16_blend(dp, blocks, st); else if (ctx->engine == 0) launch_decode_v2(lanes, ctx->prefetch, dp, blocks, st); else if (ctx->lanes_per_stream == 16) launch_decode16(dp, blocks, st); else launch_decode32(dp, blocks, st); }
     if (dbg) { CK(cudaStreamSynchronize(st)); fprintf(stderr, "divans_b200[debug]: decode kernel ok (blocks=%u, lps=%d)\n", blocks, ctx->lanes_per_stream); }
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaEventRecord(ctx->ev_busy, st)); ctx->busy_recorded = true;
@@ -470,7 +475,7 @@ static DivansResult encode_device_internal(divans_b200_ctx *ctx, size_t n, int r
     CK(cudaMemsetAsync(ctx->d_counter, 0, 4, st));
     CK(cudaEventRecord(ctx->ev0, st));
     CK(cudaEventRecord(ctx->evm, st));
-    launch_encode_model(ep, blocks, st);
+    if (o->cdf_model == DIVANS_B200_CDF_BLEND) launch_encode_model_blend(ep, blocks, st); else launch_encode_model(ep, blocks, st);
     CK(cudaEventRecord(ctx->evm1, st));
     launch_encode_flush_mux(ep, st);
     CK(cudaEventRecord(ctx->ev1, st));

@@ -2,6 +2,7 @@
 // and the encoder's model pass (dv_encode.cu).
 #pragma once
 #include "dv_engine_kernel.cuh"
+#include "dv_blend.cuh"
 #include "dv_kernels.h"
 
 namespace dv {
@@ -424,6 +425,13 @@ __device__ __forceinline__ void literal_fast(St &s, Next &nx, const G2 g, const 
         lit_context(s);
         enter_lit_nibble<ENC, true>(s, nx);
     }
+}
+
+// the nibble core of the kernel's probability model
+template <bool ENC, int LPS, bool BLEND>
+__device__ __forceinline__ int core_dispatch(St &s, const Next &nx, const G2 g, const bool writer) {
+    if constexpr (BLEND) return nibble_core_blend<ENC, LPS>(s, nx, g, writer);
+    else return nibble_core<ENC, LPS>(s, nx, g, writer);
 }
 
 }  // namespace dv

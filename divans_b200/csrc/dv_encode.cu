@@ -14,7 +14,7 @@
 
 namespace dv {
 
-template <int LPS>
+template <int LPS, bool BLEND = false>
 __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(EncodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
     g.gmask = (LPS == 16) ? (0xffffu << (lane & 16)) : 0xffffffffu;
     g.store0 = (LPS == 16) ? ((lane & 15) == 0) : (lane == 0);
     g.nl = 16;
+    g.grp = group_in_block;
+    g.blend = BLEND;
     const bool writer = (LPS == 16) ? true : (lane < 16);
 
     St s;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
                     bool ok = true;
                     s.c->sidx = v;
                     s.out_pos = 0;
-                    reset_slot(g, s.slot, s.c->bitmaps);
+                    reset_slot(g, s.slot);
                     st_reset(s);
                     // CrossCommandBookKeeping::new, codec/interface.rs:360-366
                     uint32_t dcm = (uint32_t)p.dynamic_context_mixing;
@@ -104,13 +106,13 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
             if (__all_sync(FULL, exhausted && s.state == S_IDLE)) break;
             __syncwarp();
         }
-        if (__all_sync(FULL, s.state == S_LIT_HI)) {
+        if (!BLEND && __all_sync(FULL, s.state == S_LIT_HI)) {
             literal_fast<true, LPS>(s, nx, g, writer);
             if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); s.c->in.pos++; enter_cmd_type<true>(s, nx); }
             continue;
         }
         const bool busy = s.state != S_IDLE;
-        int sym = nibble_core<true, LPS>(s, nx, g, writer);
+        int sym = core_dispatch<true, LPS, BLEND>(s, nx, g, writer);
         if (!busy) s.cur.left = 0;
         else {
             // log overflow cannot happen for command lists whose sizes match the header; guard hostile blobs anyway
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) encode_model_kernel(E
     }
 }
 
+#ifndef DV_BLEND   // (the rANS / mux passes do not depend on the probability model: they live in the default translation unit)
 // ---------------------------------------------------------------------------------------------------------------
 // reverse rANS pass.  thread <-> (stream, chunk record)
 // ---------------------------------------------------------------------------------------------------------------
@@ -366,6 +369,14 @@ __global__ void __launch_bounds__(128) encode_mux_kernel(EncodeParams p) {
     }
 }
 
+#endif  // !DV_BLEND
+
+#ifdef DV_BLEND
+void launch_encode_model_blend(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st) {
+    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP;
+    encode_model_kernel<16, true><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
+}
+#else
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st) {
     size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP;
     encode_model_kernel<16><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
@@ -386,5 +397,7 @@ int encode_max_blocks_per_sm() {
     const int nb = stream_kernel_blocks_per_sm(encode_model_kernel<16>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
     return nb;
 }
+
+#endif  // DV_BLEND
 
 }  // namespace dv

@@ -146,7 +146,17 @@ struct G2 {            // lane geometry of one lane-group (16 lanes: one CDF ele
     unsigned gmask;    // this group's lanes
     bool store0;       // lane that performs the group's scalar stores
     int nl;            // lanes that share the group's loops: 16 or 8
+    int grp;           // index of the group inside its block (= of its cold state in dynamic shared memory)
+    bool blend;        // probability model: false = FrequentistCDF16, true = BlendCDF16 (dv_blend.cuh); a kernel template constant
 };
+
+// The group's cold state, found from scratch.  The out-of-line helpers below use this instead of taking pointers into it: a
+// generic pointer to shared memory costs two special-register reads to build, and the compiler builds the arguments of those
+// (rare) calls at the head of every iteration of the main loop (~25 instructions per iteration, profiles/r2_v6_z4096).
+__device__ __forceinline__ Cold *cold_of_group(const G2 g) {
+    extern __shared__ __align__(16) uint8_t dv_dynamic_smem[];
+    return reinterpret_cast<Cold *>(dv_dynamic_smem + (unsigned)g.grp * ((sizeof(Cold) + 15) / 16 * 16));
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // out-of-line helpers (take plain values, never a reference to St)
@@ -154,11 +164,13 @@ struct G2 {            // lane geometry of one lane-group (16 lanes: one CDF ele
 __device__ __forceinline__ void store_default_cdfs(const G2 g, int16_t *base, uint32_t n_cdfs) {
     const uint4 lo = make_uint4(0x00080004u, 0x0010000cu, 0x00180014u, 0x0020001cu);   // [4,8,...,64], frequentist_cdf.rs:17-23
     const uint4 hi = make_uint4(0x00280024u, 0x0030002cu, 0x00380034u, 0x0040003cu);
+    const uint4 z = make_uint4(0, 0, 0, 0);                                              // BlendCDF16::default(), blend_cdf.rs:128-136
     uint4 *p = reinterpret_cast<uint4 *>(base);
     uint32_t n16 = n_cdfs * 2;
-    for (uint32_t i = g.l16; i < n16; i += g.nl) p[i] = (i & 1) ? hi : lo;
+    for (uint32_t i = g.l16; i < n16; i += g.nl) p[i] = g.blend ? z : ((i & 1) ? hi : lo);
 }
-static __device__ __noinline__ void init_slab32(const G2 g, int16_t *p, uint32_t *bm, uint32_t idx) {
+static __device__ __noinline__ void init_slab32(const G2 g, int16_t *p, uint32_t first_word, uint32_t idx) {
+    uint32_t *bm = cold_of_group(g)->bitmaps + first_word;
     store_default_cdfs(g, p, 32);
     __syncwarp(g.gmask);
     if (g.store0) bm[idx >> 5] |= 1u << (idx & 31);
@@ -166,12 +178,12 @@ static __device__ __noinline__ void init_slab32(const G2 g, int16_t *p, uint32_t
 }
 __device__ __forceinline__ int16_t *ctype_slab(const St &s, const G2 g, uint32_t ctype) {
     int16_t *p = reinterpret_cast<int16_t *>(s.slot + OFF_CTYPE) + (size_t)ctype * 32 * 16;
-    if (!((s.c->bitmaps[48 + (ctype >> 5)] >> (ctype & 31)) & 1u)) init_slab32(g, p, s.c->bitmaps + 48, ctype);
+    if (!((s.c->bitmaps[48 + (ctype >> 5)] >> (ctype & 31)) & 1u)) init_slab32(g, p, 48, ctype);
     return p;
 }
 __device__ __forceinline__ int16_t *dprior_slab(const St &s, const G2 g, uint32_t prior) {
     int16_t *p = reinterpret_cast<int16_t *>(s.slot + OFF_DPRIOR) + (size_t)prior * 32 * 16;
-    if (!((s.c->bitmaps[56 + (prior >> 5)] >> (prior & 31)) & 1u)) init_slab32(g, p, s.c->bitmaps + 56, prior);
+    if (!((s.c->bitmaps[56 + (prior >> 5)] >> (prior & 31)) & 1u)) init_slab32(g, p, 56, prior);
     return p;
 }
 __device__ __forceinline__ uint32_t get_distance_prior(const St &s, uint32_t copy_len) {   // codec/interface.rs:426-430
@@ -182,7 +194,8 @@ __device__ __forceinline__ uint32_t get_distance_prior(const St &s, uint32_t cop
 
 // Default-initialise every literal-prior slab the current context map / mixing mask can reach; returns the uniform
 // mixing value (or -1).  Every lane scans the maps itself (no collectives: this runs in divergent transition code).
-static __device__ __noinline__ int ensure_literal_slabs(const G2 g, uint8_t *slot, uint32_t *bitmaps, bool mixing_trait) {
+static __device__ __noinline__ int ensure_literal_slabs(const G2 g, uint8_t *slot, bool mixing_trait) {
+    uint32_t *bitmaps = cold_of_group(g)->bitmaps;
     uint32_t mx4 = 0;
     const uint4 *m4 = reinterpret_cast<const uint4 *>(slot + OFF_LCM);
     for (uint32_t i = 0; i < 1024; i++) {
@@ -237,7 +250,8 @@ static __device__ __noinline__ int ensure_literal_slabs(const G2 g, uint8_t *slo
 
 // 8-lane engine: what ensure_literal_slabs finds out without initialising anything (the literal priors are tagged):
 // the uniform mixing value (or -1); the context-map priors of dynamic context mixing >= 2 are still defaulted eagerly, once.
-static __device__ __noinline__ int scan_literal_config(const G2 g, uint8_t *slot, uint32_t *bitmaps, bool mixing_trait) {
+static __device__ __noinline__ int scan_literal_config(const G2 g, uint8_t *slot, bool mixing_trait) {
+    uint32_t *bitmaps = cold_of_group(g)->bitmaps;
     uint32_t present = 0;
     const uint4 *x4 = reinterpret_cast<const uint4 *>(slot + OFF_MIX);
     for (uint32_t i = 0; i < 512; i++) {
@@ -268,7 +282,8 @@ static __device__ __noinline__ void v2_clear_literal_tables(const G2 g, uint8_t 
 // v2 engine: a stream whose speeds can wrap i16 counters needs all 16 bits of every element.  Priors of the current generation
 // lose their tag bits, every other prior becomes the default CDF, and every slab is marked initialised (the bitmaps the
 // round-1 engine uses).  From here on the stream's literal priors are plain i16 arrays.
-static __device__ __noinline__ void v2_make_untagged(const G2 g, uint8_t *slot, uint32_t *bitmaps, uint32_t gen) {
+static __device__ __noinline__ void v2_make_untagged(const G2 g, uint8_t *slot, uint32_t gen) {
+    uint32_t *bitmaps = cold_of_group(g)->bitmaps;
     uint32_t *p = reinterpret_cast<uint32_t *>(slot + OFF_LIT_HI);
     const uint32_t n_cdf = (uint32_t)(2 * LIT_TABLE_CDFS);
     for (uint32_t c = (uint32_t)g.l16; c < n_cdf; c += (uint32_t)g.nl) {     // one CDF (8 words) per lane and step
@@ -286,20 +301,25 @@ static __device__ __noinline__ void v2_make_untagged(const G2 g, uint8_t *slot, 
 // fresh arena state for a new stream: zero the maps (ffi/alloc_util.rs:70-99), clear slab bitmaps, default the dense priors
 // Slot header words (OFF_HDR, persistent): [0] generation counter, [1] literal tables may hold untagged 16-bit values,
 // [2] literal-context-map bytes written since the map was last zeroed, [3] the mixing mask holds values of an earlier stream.
-static __device__ __noinline__ void reset_slot(const G2 g, uint8_t *slot, uint32_t *bitmaps) {
+static __device__ __noinline__ void reset_slot(const G2 g, uint8_t *slot) {
+    uint32_t *bitmaps = cold_of_group(g)->bitmaps;
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *p = reinterpret_cast<uint4 *>(slot + OFF_LCM);
     for (uint32_t i = g.l16; i < (16384 + 8192 + 1024) / 16; i += g.nl) p[i] = z;   // lcm, mix, dcm are contiguous
     for (uint32_t i = g.l16; i < 65; i += g.nl) bitmaps[i] = 0;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(slot + OFF_MISC), (uint32_t)MISC_CDFS);
-    if (g.store0) { uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR); hdr[2] = 0; hdr[3] = 0; }
+    if (g.store0) {
+        uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR); hdr[2] = 0; hdr[3] = 0;
+        if (g.blend) hdr[1] = 1u;   // blend priors keep their step count in sign bits: the v2 engine must wipe before trusting tags
+    }
     __syncwarp(g.gmask);
 }
 // v2 engine: the same fresh state without streaming 25 KB of zeros through L2 per stream.  Only the part of the literal context
 // map that earlier streams wrote is zeroed (header word 2: 64 bytes for the usual one-block-type map); the mixing mask is
 // left alone until it is needed -- a PredictionMode command rewrites all 8192 values, a literal that arrives before any
 // such command zeroes it first (v2_mix_before_use).
-static __device__ __noinline__ void reset_slot_v2(const G2 g, uint8_t *slot, uint32_t *bitmaps) {
+static __device__ __noinline__ void reset_slot_v2(const G2 g, uint8_t *slot) {
+    uint32_t *bitmaps = cold_of_group(g)->bitmaps;
     uint32_t *hdr = reinterpret_cast<uint32_t *>(slot + OFF_HDR);
     const uint4 z = make_uint4(0, 0, 0, 0);
     const uint32_t lcm16 = (min(hdr[2], 16384u) + 15u) / 16u;
@@ -341,7 +361,8 @@ static __device__ __noinline__ void replay_copy(const G2 g, uint8_t *out, uint32
 
 // dictionary word + RFC 7932 transform into `scratch` by the group's first lane (cmd_to_raw/mod.rs:284-309; the
 // transform itself is the brotli crate's TransformDictionaryWord, NOT-IN-TREE); returns the length or -1
-static __device__ __noinline__ int dict_word(const uint8_t *tb, uint8_t *o, uint32_t word_size, uint32_t word_id, uint32_t transform) {
+static __device__ __noinline__ int dict_word(const G2 g, const uint8_t *tb, uint32_t word_size, uint32_t word_id, uint32_t transform) {
+    uint8_t *o = cold_of_group(g)->scratch;
     if (word_size < 4 || word_size > 24 || transform >= 121) return -1;
     uint64_t widx = (uint64_t)word_id * word_size + reinterpret_cast<const uint32_t *>(tb + TB_OFFSETS)[word_size];
     if (widx + word_size > TB_DICT_SIZE) return -1;

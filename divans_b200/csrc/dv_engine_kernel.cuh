@@ -123,7 +123,7 @@ __device__ __forceinline__ void start_literal(St &s, Next &nx, const G2 g, uint3
     if (!s.c->lit_slabs_ready) {
         if (V2 && !s.c->pm_seen) v2_mix_before_use(g, s.slot);   // no PredictionMode command yet: the mask must read as zeros
         // v2 engine: literal priors carry generation tags and read as the default CDF until first written: nothing to initialise
-        int u = (V2 && s.tagged) ? scan_literal_config(g, s.slot, s.c->bitmaps, s.mixing_trait) : ensure_literal_slabs(g, s.slot, s.c->bitmaps, s.mixing_trait);
+        int u = (V2 && s.tagged) ? scan_literal_config(g, s.slot, s.mixing_trait) : ensure_literal_slabs(g, s.slot, s.mixing_trait);
         s.lit_cfg = u >= 0 ? mm_cfg((uint32_t)u) : -1; s.c->lit_slabs_ready = true;
     }
     s.l8 = reseed_last8(s);
@@ -436,12 +436,11 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
     case S_DC_TR_LO: {
         uint32_t tr = (s.f3 << 4) | (uint32_t)nib;
         if (tr >= 121) { s.status = ST_FAIL; return; }   // DictTransformIndexUndefined
-        uint8_t *scratch = s.c->scratch;
-        int n = dict_word(s.tables, scratch, s.f0, s.f2, tr);   // every lane computes the same bytes (benign duplicate writes)
+        int n = dict_word(g, s.tables, s.f0, s.f2, tr);   // every lane computes the same bytes (benign duplicate writes)
         if (n < 0) { s.status = ST_FAIL; return; }
         __syncwarp(g.gmask);
         if ((uint64_t)n > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
-        for (int i = g.l16; i < n; i += g.nl) s.out[s.out_pos + i] = scratch[i];
+        for (int i = g.l16; i < n; i += g.nl) s.out[s.out_pos + i] = s.c->scratch[i];
         __syncwarp(g.gmask);
         s.out_pos += (uint32_t)n;
         tail = 1;
@@ -506,7 +505,7 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
             s.c->ad_cm_lo = f8_pair_to_speed((uint32_t)(a >> 32) & 0xff, (uint32_t)(a >> 40) & 0xff);
             s.c->ad_cm_hi = f8_pair_to_speed((uint32_t)(a >> 48) & 0xff, (uint32_t)(a >> 56) & 0xff);
             s.speeds_small = speed_is_small(s.ad_stride) && speed_is_small(s.c->ad_cm_lo) && speed_is_small(s.c->ad_cm_hi);
-            if (V2 && !s.speeds_small && s.tagged) { v2_make_untagged(g, s.slot, s.c->bitmaps, s.gen); s.tagged = false; }
+            if (V2 && !s.speeds_small && s.tagged) { v2_make_untagged(g, s.slot, s.gen); s.tagged = false; }
             if (!V2 && !s.speeds_small && g.store0) reinterpret_cast<uint32_t *>(s.slot + OFF_HDR)[1] = 1u;   // elements may use their sign bits: the v2 engine must wipe before trusting tags
             s.c->lit_slabs_ready = false; s.c->t2_dirty = true; s.c->pm_seen = true;
             tail = 1;

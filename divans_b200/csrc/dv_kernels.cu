@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128) demux_kernel(FrameParams p, uint8_t *payl
 // stream kernel: persistent warps, two streams per warp in lock step (dv_engine.cuh), work pulled from a global counter.
 // LPS == 32 keeps the north-star "one warp owns one stream" layout: the upper half-warp mirrors the lower one.
 // ---------------------------------------------------------------------------------------------------------------
-template <int LPS>
+template <int LPS, bool BLEND = false>
 __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
     g.gmask = (LPS == 16) ? (0xffffu << (lane & 16)) : 0xffffffffu;
     g.store0 = (LPS == 16) ? ((lane & 15) == 0) : (lane == 0);
     g.nl = 16;
+    g.grp = group_in_block;
+    g.blend = BLEND;
     const bool writer = (LPS == 16) ? true : (lane < 16);
 
     St s;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
                     uint64_t cap = p.out_cap[v];
                     s.c->out_cap = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap; s.out_pos = 0;
                     s.c->ring_len = 1u << in[5];
-                    reset_slot(g, s.slot, s.c->bitmaps);
+                    reset_slot(g, s.slot);
                     st_reset(s);
                     coder_init_dec(s.cur, reinterpret_cast<const uint32_t *>(pl), pay0 >> 2);   // command stream (CMD_CODER, codec/interface.rs:49)
                     coder_init_dec(s.c->oth, reinterpret_cast<const uint32_t *>(pl + (((uint64_t)pay0 + 15) & ~15ull)), pay1 >> 2);   // literal stream (LIT_CODER, :50)
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
             __syncwarp();
         }
         // ---- one nibble per group ----
-        if (__all_sync(FULL, s.state == S_LIT_HI)) {
+        if (!BLEND && __all_sync(FULL, s.state == S_LIT_HI)) {   // (the fast loops are frequentist arithmetic)
             literal_fast<false, LPS>(s, nx, g, writer);
             if (s.cur.underflow) s.status = ST_NEED_INPUT;
             if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); enter_cmd_type<false>(s, nx); }
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(DECODE_BLOCK_THREADS, 8) decode_kernel(DecodeP
             continue;
         }
         const bool busy = s.state != S_IDLE;
-        int sym = nibble_core<false, LPS>(s, nx, g, writer);
+        int sym = core_dispatch<false, LPS, BLEND>(s, nx, g, writer);
         // ---- per-group scalar state machines (divergent) ----
         if (busy) {
             if (s.cur.underflow) s.status = ST_NEED_INPUT;
@@ -260,6 +262,15 @@ void launch_decode32(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) 
 int decode_max_blocks_per_sm32() {
     const int nb = stream_kernel_blocks_per_sm(decode_kernel<32>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 32) * SMEM_BYTES_PER_GROUP);
     return nb;
+}
+#elif defined(DV_BLEND)
+// the reference's feature="blend" probability model (dv_blend.cuh): its own translation unit, 16 lanes per stream
+void launch_decode16_blend(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {
+    size_t smem = (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP;
+    decode_kernel<16, true><<<n_blocks, DECODE_BLOCK_THREADS, smem, st>>>(p);
+}
+int decode_max_blocks_per_sm16_blend() {
+    return stream_kernel_blocks_per_sm(decode_kernel<16, true>, DECODE_BLOCK_THREADS, (size_t)(DECODE_BLOCK_THREADS / 16) * SMEM_BYTES_PER_GROUP);
 }
 #else
 void launch_decode16(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st) {

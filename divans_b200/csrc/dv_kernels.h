@@ -27,5 +27,9 @@ int decode_max_blocks_per_sm16();
 void launch_encode_model(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);   // groups of 16 lanes
 void launch_encode_flush_mux(const EncodeParams &p, cudaStream_t st);                  // reverse rANS + mux/CRC (2 launches)
 int encode_max_blocks_per_sm();
+// the reference's feature="blend" probability model (dv_blend.cuh): 16 lanes per stream, generic nibble path only
+void launch_decode16_blend(const DecodeParams &p, uint32_t n_blocks, cudaStream_t st);
+int decode_max_blocks_per_sm16_blend();
+void launch_encode_model_blend(const EncodeParams &p, uint32_t n_blocks, cudaStream_t st);
 void launch_rcp15_init(uint64_t *tab, cudaStream_t st);
 }  // namespace dv

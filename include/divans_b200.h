@@ -110,6 +110,14 @@ typedef struct divans_b200_ctx divans_b200_ctx;
 #define DIVANS_B200_MODEL_CURRENT 0
 #define DIVANS_B200_MODEL_WASM_2018 1
 #define DIVANS_B200_FLAG_MODEL_WASM_2018 4u
+/* Probability model.  Default = FrequentistCDF16, what every build of the reference uses unless it is compiled with
+ * feature="blend", which swaps in BlendCDF16 for the whole crate (src/interface.rs:146-147, probability/blend_cdf.rs:109-208:
+ * a division-free model that averages towards the coded symbol with a decaying rate and ignores the speeds).  Nothing in a
+ * stream says which model coded it: the two sides have to agree, as with the reference's compile-time switch.  Blend streams
+ * run on the generic per-nibble path (16 lanes per stream), not on the literal fast loops. */
+#define DIVANS_B200_CDF_FREQUENTIST 0
+#define DIVANS_B200_CDF_BLEND 1
+#define DIVANS_B200_FLAG_CDF_BLEND 8u
 
 /* per-stream status values are DivansResult codes (0 ok, 1 truncated input, 2 output capacity too small, 3 corrupt) */
 
@@ -179,6 +187,7 @@ typedef struct {
     int32_t literal_pred_mode;      /* internal literal-only compressor: LSB6=0 MSB6=1 UTF8=2 SIGN=3 */
     int32_t literal_mixing_value;   /* internal literal-only compressor: value of all 8192 mixing entries (reference: 4) */
     int32_t model_rev;              /* DIVANS_B200_MODEL_CURRENT (default) or DIVANS_B200_MODEL_WASM_2018 */
+    int32_t cdf_model;              /* DIVANS_B200_CDF_FREQUENTIST (default) or DIVANS_B200_CDF_BLEND */
 } divans_b200_encode_options;
 void divans_b200_encode_options_default(divans_b200_encode_options *o);
 

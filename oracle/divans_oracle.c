@@ -98,6 +98,66 @@ int32_t dvo_fast_divide(int32_t num, int16_t denom) {
     return fast_divide_30bit_by_16bit(num, inv, sh);
 }
 
+#ifdef DVO_FEATURE_BLEND
+/* ------------------------------------------------------------------------------------------
+ * BlendCDF16  (probability/blend_cdf.rs:109-208; generic BaseCDF paths probability/interface.rs:97-108,136-198)
+ * ------------------------------------------------------------------------------------------ */
+#define BLEND_CDF_MAX 32767                 /* probability/interface.rs:429 */
+#define BLEND_DEL (BLEND_CDF_MAX - 16)      /* blend_cdf.rs:80,90 */
+int dvo_feature_blend(void) { return 1; }
+void dvo_cdf_default(dvo_cdf16 *c) { memset(c->c, 0, sizeof c->c); c->mix_rate = (1 << 10) + (1 << 9); c->count = 0; }   /* blend_cdf.rs:128-136 */
+
+/* mul_blend (:15-55) + the early-growth step (:116-124) */
+static void blend_internal(dvo_cdf16 *c, const int16_t to_blend[16], int32_t mix_rate) {
+    const int32_t bias = (c->count & 0xf) << (15 - 4);
+    const int32_t scale_minus_blend = (1 << 15) - mix_rate;
+    for (int i = 0; i < 16; i++) {
+        int32_t e = (int32_t)((uint32_t)(int32_t)to_blend[i] * (uint32_t)mix_rate);
+        e = (int32_t)((uint32_t)e + (uint32_t)(int32_t)c->c[i] * (uint32_t)scale_minus_blend + (uint32_t)bias);
+        c->c[i] = (int16_t)(e >> 15);
+    }
+    if (c->c[15] < (int16_t)(BLEND_DEL - (c->c[15] >> 1)))
+        for (int i = 0; i < 16; i++) c->c[i] = (int16_t)(c->c[i] + (c->c[i] >> 1));
+}
+int16_t dvo_cdf_value(const dvo_cdf16 *c, uint8_t sym) {   /* :160-171: the bias is the latent uniform distribution */
+    if (sym == 15) return BLEND_CDF_MAX;
+    int16_t bias = (int16_t)(BLEND_CDF_MAX - c->c[15]);
+    return (int16_t)(c->c[sym] + (int16_t)(((int32_t)bias * (int32_t)(sym + 1)) >> 4));
+}
+void dvo_cdf_sym_start_freq(const dvo_cdf16 *c, uint8_t sym, int16_t *start, int16_t *freq) {
+    /* probability/interface.rs:97-108 with div_by_max = >> log_max = >> 15 (blend_cdf.rs:154-159) */
+    int32_t cdf_sym = ((int32_t)dvo_cdf_value(c, sym & 15) << 15) >> 15;
+    int32_t cdf_prev = sym ? ((int32_t)dvo_cdf_value(c, (uint8_t)((sym - 1) & 15)) << 15) >> 15 : 0;
+    int32_t f = cdf_sym - cdf_prev;
+    *start = (int16_t)((int16_t)cdf_prev + 1);
+    *freq = (int16_t)((int16_t)f - 1);
+}
+uint8_t dvo_cdf_lookup(const dvo_cdf16 *c, int16_t cdf_offset, int16_t *start, int16_t *freq) {
+    /* probability/interface.rs:136-198 (max() = CDF_MAX) */
+    int16_t r = (int16_t)(((int32_t)cdf_offset * (int32_t)BLEND_CDF_MAX) >> 15);
+    uint8_t sym = 15;
+    for (uint8_t i = 0; i < 15; i++) {
+        if (r < dvo_cdf_value(c, i)) { sym = i; break; }
+    }
+    dvo_cdf_sym_start_freq(c, sym, start, freq);
+    return sym;
+}
+void dvo_cdf_blend(dvo_cdf16 *c, uint8_t sym, dvo_speed s) {
+    /* blend_cdf.rs:186-208: the speed is computed and NOT used (`_mix_rate`); the CDF's own decaying mix_rate is */
+    (void)s;
+    c->count = (int32_t)((uint32_t)c->count + 1u);
+    int16_t to_blend[16];
+    for (int i = 0; i < 16; i++) to_blend[i] = i >= sym ? BLEND_DEL : 0;   /* to_blend_lut :87-108 */
+    blend_internal(c, to_blend, c->mix_rate);
+    c->mix_rate -= c->mix_rate >> 7;
+}
+void dvo_cdf_average(const dvo_cdf16 *self, const dvo_cdf16 *other, int32_t mix_rate, dvo_cdf16 *out) {
+    /* blend_cdf.rs:181-185 */
+    *out = *self;
+    blend_internal(out, other->c, mix_rate);
+}
+#else
+int dvo_feature_blend(void) { return 0; }
 /* ------------------------------------------------------------------------------------------
  * FrequentistCDF16  (probability/frequentist_cdf.rs:12-86, probability/interface.rs:97-198)
  * ------------------------------------------------------------------------------------------ */
@@ -152,6 +212,8 @@ void dvo_cdf_average(const dvo_cdf16 *self, const dvo_cdf16 *other, int32_t mix_
         out->c[i] = (int16_t)((int32_t)acc >> 15);
     }
 }
+
+#endif /* DVO_FEATURE_BLEND */
 
 /* probability/interface.rs:566-585 (i16 versions) */
 uint8_t dvo_speed_to_u8(int16_t data) {
@@ -1357,7 +1419,8 @@ static const char *next_tok(const char *p, const char *end, const char **tok, si
 }
 static int tok_is(const char *t, size_t tl, const char *s) { return strlen(s) == tl && memcmp(t, s, tl) == 0; }
 static int tok_num(const char *t, size_t tl, long long *v) {
-    if (tl == 0 || tl > 18) return 0; long long r = 0; size_t i = 0; int neg = 0;
+    if (tl == 0 || tl > 18) return 0;
+    long long r = 0; size_t i = 0; int neg = 0;
     if (t[0] == '-') { neg = 1; i = 1; if (tl == 1) return 0; }
     for (; i < tl; i++) { if (t[i] < '0' || t[i] > '9') return 0; r = r * 10 + (t[i] - '0'); }
     *v = neg ? -r : r; return 1;
@@ -1497,12 +1560,14 @@ static void *batch_worker(void *arg) {
     return NULL;
 }
 static int run_batch(batch_job *j, int n_threads) {
-    if (n_threads < 1) n_threads = 1; if (n_threads > 256) n_threads = 256;
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
     volatile size_t next = 0; j->next = &next;
     if (!crc_table_ready) crc_init_table();
     pthread_t th[256];
     for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, batch_worker, j);
     for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    j->next = NULL;   /* (the counter lives in this frame: no pointer to it survives the call) */
     int bad = 0; for (size_t i = 0; i < j->n; i++) if (j->status[i] != DVO_SUCCESS) bad++;
     return bad;
 }

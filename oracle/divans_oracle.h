@@ -46,9 +46,20 @@ extern "C" {
 #define DVO_NEEDS_MORE_OUTPUT 2
 #define DVO_FAILURE 3
 
-/* ---- probability model: reference src/probability/frequentist_cdf.rs ---- */
+/* ---- probability model: reference src/probability/frequentist_cdf.rs.  Compiled with -DDVO_FEATURE_BLEND (the second library
+ * oracle/_build/libdivans_oracle_blend.so) the model is the reference's feature="blend" instead: BlendCDF16,
+ * src/probability/blend_cdf.rs:109-208, selected for the whole crate by src/interface.rs:146-147.  A compile-time switch
+ * there, a compile-time switch here: nothing in a stream says which model coded it.  Parity of the blend model: the
+ * reference holds no stream coded with it; it is pinned by restating the four tests the reference runs on BlendCDF16
+ * (probability/common_tests.rs:4-110 through blend_cdf.rs:213) -- tests/test_oracle_kat.py -- i.e. at property level only. ---- */
+#ifdef DVO_FEATURE_BLEND
+typedef struct { int16_t c[16]; int32_t mix_rate, count; } dvo_cdf16;
+int16_t dvo_cdf_value(const dvo_cdf16 *c, uint8_t sym);    /* BaseCDF::cdf(), blend_cdf.rs:160-171 */
+#else
 typedef struct { int16_t c[16]; } dvo_cdf16;
+#endif
 typedef struct { int16_t inc, lim; } dvo_speed;
+int dvo_feature_blend(void);                                /* 1 in the blend library */
 
 void dvo_cdf_default(dvo_cdf16 *c);
 void dvo_cdf_blend(dvo_cdf16 *c, uint8_t sym, dvo_speed s);

@@ -10,7 +10,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "libdivans_oracle.so")
+# "" = the reference's default probability model; "blend" = its feature="blend" build (oracle/oracle_blend.py loads this same
+# module a second time with _VARIANT preset: a compile-time switch in the reference, a second library here)
+_VARIANT = globals().get("_VARIANT", "")
+_LIB_PATH = os.path.join(_HERE, "_build", "libdivans_oracle%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 SUCCESS, NEEDS_MORE_INPUT, NEEDS_MORE_OUTPUT, FAILURE = 0, 1, 2, 3
 
@@ -28,7 +31,7 @@ class Speed(ctypes.Structure):
 
 
 class Cdf16(ctypes.Structure):
-    _fields_ = [("c", ctypes.c_int16 * 16)]
+    _fields_ = [("c", ctypes.c_int16 * 16)] + ([("mix_rate", ctypes.c_int32), ("count", ctypes.c_int32)] if _VARIANT == "blend" else [])
 
 
 class Options(ctypes.Structure):
@@ -96,6 +99,10 @@ def lib():
         L.dvo_cdf_blend.argtypes = [ctypes.POINTER(Cdf16), ctypes.c_uint8, Speed]
         L.dvo_cdf_average.argtypes = [ctypes.POINTER(Cdf16), ctypes.POINTER(Cdf16), ctypes.c_int32, ctypes.POINTER(Cdf16)]
         L.dvo_weights_update.argtypes = [ctypes.POINTER(Weights), ctypes.c_int16, ctypes.c_int16, ctypes.c_int16]
+        assert L.dvo_feature_blend() == (1 if _VARIANT == "blend" else 0)
+        if _VARIANT == "blend":
+            L.dvo_cdf_value.argtypes = [ctypes.POINTER(Cdf16), ctypes.c_uint8]
+            L.dvo_cdf_value.restype = ctypes.c_int16
         u64p = ctypes.c_void_p
         L.dvo_decode_batch.argtypes = [u8p, u64p, u64p, u8p, u64p, u64p, u64p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
         L.dvo_encode_raw_batch.argtypes = [u8p, u64p, u64p, u8p, u64p, u64p, u64p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,

@@ -20,6 +20,14 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def oracle_blend():
+    """the oracle compiled with the reference's feature="blend" probability model (oracle/oracle_blend.py)"""
+    from oracle import oracle_blend as ob
+    ob.build()
+    return ob
+
+
+@pytest.fixture(scope="session")
 def golden():
     import json
     d = os.path.join(ROOT, "tests", "golden")
