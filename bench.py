@@ -221,7 +221,7 @@ def run_reference_arm(args):
     return 0
 
 
-def _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, raw_blob, off, ln, steps):
+def _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, raw_blob, off, ln, steps, flags=0):
     """device-resident decode of one population: K steps timed with CUDA events on `stream`; returns (ms per step, decode-kernel
     ms, bit-exact vs the raw input)"""
     n = len(coff)
@@ -233,7 +233,7 @@ def _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, raw_blob, off, 
 
     def step():
         eng.decode_batch_device(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
-                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, d_in.numel(), 0, stream.cuda_stream)
+                                d_out_cap.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(), n, d_in.numel(), flags, stream.cuda_stream)
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -268,14 +268,14 @@ def measure_populations(eng, torch, dev, stream, blob, off, ln, steps=3):
     out = np.zeros(int(cap.sum()), np.uint8)
     pops = {}
 
-    def run(name, desc, opts, cmds=None):
+    def run(name, desc, opts, cmds=None, flags=0):
         if cmds is None:
             out_len, status = eng.encode_batch_host(blob, off, ln, out, eoff, cap, opts)
         else:
             out_len, status = eng.encode_batch_host(cmds[0], cmds[1], cmds[2], out, eoff, cap, opts, cmds=True)
         assert (status == 0).all(), name
         comp, coff, clen = _compact(out, eoff, out_len)
-        ms, kms, ok = _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, blob, off, ln, steps)
+        ms, kms, ok = _device_decode_ms(eng, torch, dev, stream, comp, coff, clen, blob, off, ln, steps, flags)
         pops[name] = {"encoding": desc, "ms_per_step": ms, "decode_kernel_ms": kms, "value": float(ln.sum()) / ms / 1e3, "unit": UNIT,
                       "compressed_bytes": int(clen.sum()), "bit_exact": ok, "steps": steps}
 
@@ -283,6 +283,8 @@ def measure_populations(eng, torch, dev, stream, blob, off, ln, steps=3):
         divans_b200.encode_options(window_size=16), cmds=divans_b200.lz77_cmds_batch(blob, off, ln, 16, 2, 4))
     run("L_dcm2", "literal-only, dynamic_context_mixing=2 (two priors mixed and the weights adapted per nibble)", divans_b200.encode_options(dynamic_context_mixing=2))
     run("L_utf8", "literal-only, UTF8 context mode, mixing value 1", divans_b200.encode_options(literal_pred_mode=2, literal_mixing_value=1))
+    run("L_blend", "literal-only, coded with the reference's feature=\"blend\" probability model (BlendCDF16; generic per-nibble path, no literal fast loop)",
+        divans_b200.encode_options(cdf_model=divans_b200.CDF_BLEND), flags=divans_b200.FLAG_CDF_BLEND)
     return pops
 
 

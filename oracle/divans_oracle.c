@@ -1210,6 +1210,11 @@ static int decode_impl(const uint8_t *in, size_t in_len, uint8_t *out, size_t ou
         if (s->cmd.d.underflow || s->lit.d.underflow) { rc = DVO_NEEDS_MORE_INPUT; break; }
         if (s->rc.overflow) { rc = DVO_NEEDS_MORE_OUTPUT; break; }
     }
+    /* The reference asks for input at the nibble that cannot be refilled (drain_or_fill_static_buffer, codec/interface.rs:868-917)
+     * and never decodes past it.  This restatement runs a command to its end with zero-filled states and looks at the underflow
+     * flags afterwards: an error a command reports AFTER one of its coders ran dry is a consequence of the garbage that
+     * followed, so the earlier event wins. */
+    if ((rc == DVO_FAILURE || rc == DVO_NEEDS_MORE_OUTPUT) && (s->cmd.d.underflow || s->lit.d.underflow)) rc = DVO_NEEDS_MORE_INPUT;
     *out_len = s->rc.out_len;
     if (n_cmd_nibbles) *n_cmd_nibbles = s->cmd.d.n_syms;
     if (n_lit_nibbles) *n_lit_nibbles = s->lit.d.n_syms;
