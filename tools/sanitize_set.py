@@ -1,5 +1,5 @@
 """Reduced parity set for compute-sanitizer (memcheck / racecheck / initcheck): golden fixtures, the reference-held stream,
-12 random-IR streams, one 64 KiB literal-only stream and one LZ77 stream, both lane layouts, decode and encode, every result
+12 random-IR streams, one 64 KiB literal-only stream and one LZ77 stream, all lane layouts, the blend model, decode and encode, every result
 checked against the oracle.  Usage: compute-sanitizer --tool memcheck python tools/sanitize_set.py"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,5 +36,15 @@ for lps in (8, 16, 32):
         for c, o in cmds[:6]:
             got = eng.encode([c.serialize()], divans_b200.encode_options(window_size=o.window_size, dynamic_context_mixing=o.dynamic_context_mixing), cmds=True)[0]
             assert got == c.encode(o)
+    if lps == 16:   # the reference's feature="blend" probability model: its own decode / encode kernels
+        from oracle import oracle_blend as OB
+        braws = [raw64[:20000], raw64[:1], b"", text[70000:70000 + 9000]]
+        for dcm in (0, 2):
+            bs = [OB.encode_raw(r, OB.options(dynamic_context_mixing=dcm)) for r in braws]
+            bs.append(OB.Commands.lz77(raw64[:30000], window=16).encode(OB.options(window_size=16, dynamic_context_mixing=dcm)))
+            res = eng.decode(bs, [len(r) + 64 for r in braws] + [30064], divans_b200.FLAG_CDF_BLEND)
+            assert all(st == 0 for st, _ in res) and all(out == r for (st, out), r in zip(res, braws + [raw64[:30000]]))
+            enc = eng.encode(braws, divans_b200.encode_options(dynamic_context_mixing=dcm, cdf_model=divans_b200.CDF_BLEND))
+            assert enc == bs[:len(braws)]
     eng.close()
 print("sanitize set ok: %d streams, both lane layouts, decode + encode" % len(streams))
