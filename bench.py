@@ -500,9 +500,17 @@ def main():
         g_comp = [torch.zeros(int(a[0]), dtype=torch.uint8, device=dev) if rank == 0 else None for a in all_sizes]
         g_len = [torch.zeros(int(a[1]), dtype=torch.int64, device=dev) if rank == 0 else None for a in all_sizes]
         g_off = [torch.zeros(int(a[1]), dtype=torch.int64, device=dev) if rank == 0 else None for a in all_sizes]
-        dist.gather(torch.from_numpy(comp).to(dev), g_comp if rank == 0 else None, dst=0)
-        dist.gather(torch.from_numpy(clen.astype(np.int64)).to(dev), g_len if rank == 0 else None, dst=0)
-        dist.gather(torch.from_numpy(coff.astype(np.int64)).to(dev), g_off if rank == 0 else None, dst=0)
+        # (shards differ in compressed size: point-to-point transfers, not dist.gather, which wants equal shapes)
+        mine = [torch.from_numpy(comp).to(dev), torch.from_numpy(clen.astype(np.int64)).to(dev), torch.from_numpy(coff.astype(np.int64)).to(dev)]
+        if rank == 0:
+            for dst_list, t in zip((g_comp, g_len, g_off), mine):
+                dst_list[0].copy_(t)
+            for r in range(1, world):
+                for dst_list in (g_comp, g_len, g_off):
+                    dist.recv(dst_list[r], src=r)
+        else:
+            for t in mine:
+                dist.send(t, dst=0)
         if rank == 0:
             base = np.concatenate([[0], np.cumsum([int(a[0]) for a in all_sizes])[:-1]])
             job_blob = torch.cat(g_comp).cpu().pin_memory()

@@ -229,8 +229,9 @@ __device__ __forceinline__ void blend_store_v2(const uint32_t ev, const uint32_t
     }
     store_elems<LPG>(p, g.l16, c2 | f.mytag);
 }
+// state after coding `sym` of the validated prior (ev, mv), before renormalisation (ans.rs:230-244)
 template <int LPG>
-__device__ __forceinline__ void rans_step_v2(uint64_t &st, const uint32_t ev, const uint32_t mv, const int sym, FastK &f) {
+__device__ __forceinline__ uint64_t rans_advance_v2(const uint64_t st, const uint32_t ev, const uint32_t mv, const int sym) {
     const uint32_t inv = recip32(mv);
     uint32_t hi, lo;
     const int prev = (sym - 1) & 15;
@@ -246,13 +247,23 @@ __device__ __forceinline__ void rans_step_v2(uint64_t &st, const uint32_t ev, co
     if (sym == 0) lo = 0;
     const uint32_t freq = hi - lo - 1;                                       // "major hax": start = lo + 1 (probability/interface.rs:103-104)
     const uint32_t t = ((uint32_t)st & 0x7fffu) - lo - 1;                    // 0 <= t < freq: the search put the offset in this bin
-    uint64_t x = (uint64_t)freq * (st >> 15) + (uint64_t)t;                  // ans.rs:230-244
-    if (x < (1ull << 31)) {                                                  // eager refill (dv_core.cuh literal_fast): same word order
-        x = (x << 32) | (uint64_t)f.wnext;
-        f.wi = min(f.wi + 1, f.wmax);
-        f.wnext = ld_stream_u32(f.wbase + f.wi);                             // consumed by the NEXT refill
+    return (uint64_t)freq * (st >> 15) + (uint64_t)t;
+}
+// The two rANS steps of a byte (state a: high nibble, b: low nibble), then the eager refills in payload order (a before b).  A
+// state needs a word once per ~16 nibbles of text: with 16 lanes per stream the refill code sits behind ONE warp-uniform branch
+// instead of being sixteen predicated-off instructions in every byte.
+template <int LPG>
+__device__ __forceinline__ void rans_pair_v2(uint64_t &a, uint64_t &b, const uint32_t eh, const uint32_t mh, const int h,
+                                             const uint32_t el, const uint32_t ml, const int l, FastK &f) {
+    uint64_t xa = rans_advance_v2<LPG>(a, eh, mh, h), xb = rans_advance_v2<LPG>(b, el, ml, l);
+    const bool na = xa < (1ull << 31), nb = xb < (1ull << 31);
+    // two streams per warp: no state refills in 78 % of the bytes, the branch pays (46.6 -> 45.6 ms for 4096 streams); four
+    // streams per warp: 61 %, the predicated form is the faster one (73.6 vs 75.1 ms for 8192) -- profiles/r2_v12_ab.txt
+    if (LPG == 8 || __any_sync(FULL, na || nb)) {
+        if (na) { xa = (xa << 32) | (uint64_t)f.wnext; f.wi = min(f.wi + 1, f.wmax); f.wnext = ld_stream_u32(f.wbase + f.wi); }
+        if (nb) { xb = (xb << 32) | (uint64_t)f.wnext; f.wi = min(f.wi + 1, f.wmax); f.wnext = ld_stream_u32(f.wbase + f.wi); }
     }
-    st = x;
+    a = xa; b = xb;
 }
 
 // bin search: for a monotone CDF whose last element is max (> r) the number of elements with r < c[i] is 16 - sym
@@ -297,7 +308,10 @@ __device__ __forceinline__ void mixv_finish(uint64_t &st, const MixV v, const Mi
     const int f_nb = (int)(short)((hi_pn >> 16) - (lo_pn >> 16) - 1);
     const uint32_t t = ((uint32_t)st & 0x7fffu) - lo_a - 1;
     uint64_t x = (uint64_t)(freq & 0xffffu) * (st >> 15) + (uint64_t)t;   // ans.rs:230-244
-    if (x < (1ull << 31)) { x = (x << 32) | (uint64_t)f.wnext; f.wi = min(f.wi + 1, f.wmax); f.wnext = ld_stream_u32(f.wbase + f.wi); }
+    const bool refill = x < (1ull << 31);
+    if (__any_sync(FULL, refill)) {   // (one warp-uniform branch instead of predicated-off refill code in every nibble, see rans_pair_v2)
+        if (refill) { x = (x << 32) | (uint64_t)f.wnext; f.wi = min(f.wi + 1, f.wmax); f.wnext = ld_stream_u32(f.wbase + f.wi); }
+    }
     st = x;
     weights_update32(w, f_cm, f_nb, (int)(short)freq);
     uint32_t c2 = v.cc + ((g.l16 >= sym) ? (uint32_t)cm_inc : 0u);
@@ -539,8 +553,7 @@ __device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, con
                 }
                 // -- low nibble: blend; then the rANS steps of both nibbles (state a before b: the order of the payload words)
                 blend_store_v2<LPG>(el_v, ml_v, l, pl, g, f);
-                rans_step_v2<LPG>(k.a, eh_v, mh_v, h, f);
-                rans_step_v2<LPG>(k.b, el_v, ml_v, l, f);
+                rans_pair_v2<LPG>(k.a, k.b, eh_v, mh_v, h, el_v, ml_v, l, f);
             }
             done += m;
             if (active) k.sym_count += 2 * m;
