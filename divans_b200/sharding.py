@@ -59,6 +59,7 @@ class ShardedDecoder:
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.decode_fn = decode_fn or self._engine_decode
         self.last = {}
+        self._host_out = None      # root: pinned staging buffer for the gathered output (kept between calls)
 
     def _engine_decode(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap):
         torch = self.torch
@@ -78,7 +79,8 @@ class ShardedDecoder:
 
     def decode(self, blob=None, in_off=None, in_len=None, out_cap=None):
         """root passes numpy/torch host arrays (blob uint8, in_off / in_len / out_cap uint64-like); the other ranks pass nothing.
-        Returns on root: (out uint8 tensor on host, out_off, out_len, status) -- stream i at out[out_off[i] : +out_len[i]]."""
+        Returns on root: (out uint8 tensor on host, out_off, out_len, status) -- stream i at out[out_off[i] : +out_len[i]].  On a
+        GPU job `out` is a view of a pinned staging buffer that the next call overwrites."""
         torch, dist = self.torch, self.dist
         dev, root, R, W = self.device, self.root, self.rank, self.world
         i64 = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.int64)))
@@ -142,7 +144,16 @@ class ShardedDecoder:
                         dist.P2POp(dist.irecv, st_all[parts[r][0]:parts[r][1]], r, self.group)]
             self._p2p(ops)
             self.last = dict(parts=parts, shard_bytes=[byte_hi[r] - byte_lo[r] for r in range(W)])
-            return out_all.cpu(), out_off_all.cpu(), len_all.cpu(), st_all.cpu()
+            if dev.type != "cuda":
+                return out_all, out_off_all, len_all, st_all
+            # one D2H into pinned memory (a pageable destination would cost more than the decode)
+            if self._host_out is None or self._host_out.numel() < out_all.numel():
+                self._host_out = torch.empty(out_all.numel(), dtype=torch.uint8, pin_memory=True)
+            host = self._host_out[: out_all.numel()]
+            host.copy_(out_all, non_blocking=True)
+            res = (host, out_off_all.cpu(), len_all.cpu(), st_all.cpu())
+            torch.cuda.current_stream(dev).synchronize()
+            return res
         if b > a:
             self._p2p([dist.P2POp(dist.isend, d_out[: out_hi[R] - out_lo[R]], root, self.group),
                        dist.P2POp(dist.isend, my_len, root, self.group), dist.P2POp(dist.isend, my_status, root, self.group)])
