@@ -47,7 +47,7 @@ constexpr uint64_t OFF_SLOT_END = OFF_HDR + 64;
 // the slot + offset), i.e. ONE 32-bit add in the decode loop instead of 64-bit pointer arithmetic (dv2_core.cuh).
 constexpr uint64_t SLOT_STRIDE = 16ull << 20;
 static_assert(OFF_SLOT_END <= SLOT_STRIDE, "slot layout exceeds the slot stride");
-// low-nibble prior index of the 8-lane engine: [which][index_c >> 4][index_b][index_c & 15]
+// low-nibble prior index of the v2 engine: [which][index_c >> 4][index_b][index_c & 15]
 __host__ __device__ __forceinline__ uint32_t lit_index_lo(uint32_t which, uint32_t index_c, uint32_t index_b) {
     return (which << 16) | ((index_c >> 4) << 12) | (index_b << 4) | (index_c & 15u);
 }

@@ -97,7 +97,7 @@ struct Cold {
     uint32_t lit_total;                      // v2 engine: length of the literal in flight
     bool lit_quirk;                          // v2 engine: the literal began within 8 bytes of the ring start (last_8_literals is not a plain mirror of the output)
     bool pm_seen;                            // a PredictionMode command of THIS stream has written the mixing mask
-    bool t2_dirty;                           // 8-lane engine: the slot's context table (OFF_T2) does not match lcm / mode / block type
+    bool t2_dirty;                           // v2 engine: the slot's context table (OFF_T2) does not match lcm / mode / block type
     // encoder
     CmdIn in;
     uint32_t e0, e1, e2, e3;                 // current input command fields
@@ -248,7 +248,7 @@ static __device__ __noinline__ int ensure_literal_slabs(const G2 g, uint8_t *slo
     return (present & (present - 1)) == 0 ? (__ffs(present) - 1) : -1;
 }
 
-// 8-lane engine: what ensure_literal_slabs finds out without initialising anything (the literal priors are tagged):
+// v2 engine: what ensure_literal_slabs finds out without initialising anything (the literal priors are tagged):
 // the uniform mixing value (or -1); the context-map priors of dynamic context mixing >= 2 are still defaulted eagerly, once.
 static __device__ __noinline__ int scan_literal_config(const G2 g, uint8_t *slot, bool mixing_trait) {
     uint32_t *bitmaps = cold_of_group(g)->bitmaps;

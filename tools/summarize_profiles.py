@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn the ncu artefacts of one tools/gpu_round.sh visit (gpurun_out/<tag>_*) into the committed summaries under profiles/.
+"""Turn the ncu artefacts of one tools/gpu_runs/gpu_round_r1.sh visit (gpurun_out/<tag>_*) into the committed summaries under profiles/.
 Usage: python tools/summarize_profiles.py <tag>"""
 import collections
 import csv
