@@ -560,11 +560,15 @@ def main():
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("kernel_version") == divans_b200.kernel_version() and int(tj.get("lanes_per_stream", 0)) == args.lanes and int(tj.get("streams", 0)) == n:
-                    traffic, traffic_note = tj.get("decode_kernel_dram_bytes_per_launch"), tj.get("source")
+                entries = tj.get("entries", [tj])
+                mine = [e for e in entries if int(e.get("lanes_per_stream", 0)) == args.lanes and int(e.get("streams", 0)) == n]
+                if mine and mine[0].get("kernel_version") == divans_b200.kernel_version():
+                    traffic, traffic_note = mine[0].get("decode_kernel_dram_bytes_per_launch"), mine[0].get("source")
+                elif mine:
+                    traffic_note = "profiles/traffic.json holds kernel %s for this layout, this library is %s: not reported" % (
+                        mine[0].get("kernel_version"), divans_b200.kernel_version())
                 else:
-                    traffic_note = "profiles/traffic.json is for kernel %s (%s lanes, %s streams), this library is %s: not reported" % (
-                        tj.get("kernel_version"), tj.get("lanes_per_stream"), tj.get("streams"), divans_b200.kernel_version())
+                    traffic_note = "profiles/traffic.json has no capture for %d lanes per stream x %d streams: not reported" % (args.lanes, n)
             except Exception:
                 traffic = None
         line = {

@@ -70,7 +70,14 @@ if "--traffic" in sys.argv:
     sys.path.insert(0, ROOT)
     import divans_b200
     lanes = int(sys.argv[sys.argv.index("--lanes") + 1]); streams = int(sys.argv[sys.argv.index("--streams") + 1])
-    json.dump({"decode_kernel_dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
-               "kernel_version": divans_b200.kernel_version(), "lanes_per_stream": lanes, "streams": streams,
-               "source": os.path.basename(prefix) + "_metrics.csv (ncu --set full, %d x 64 KiB streams, one launch of the decode kernel)" % streams},
-              open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    entry = {"decode_kernel_dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+             "kernel_version": divans_b200.kernel_version(), "lanes_per_stream": lanes, "streams": streams,
+             "source": os.path.basename(prefix) + "_metrics.csv (ncu --set full, %d x 64 KiB streams, one launch of the decode kernel)" % streams}
+    # one entry per (lane layout, stream count): the N = 1 and the N > 1 workloads of bench.py run different instantiations
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    entries = []
+    if os.path.exists(tp) and "--replace" not in sys.argv:
+        old = json.load(open(tp))
+        entries = old.get("entries", [old] if "kernel_version" in old else [])
+    entries = [e for e in entries if (e.get("lanes_per_stream"), e.get("streams")) != (lanes, streams)] + [entry]
+    json.dump({"entries": entries}, open(tp, "w"), indent=1)
