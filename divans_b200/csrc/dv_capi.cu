@@ -653,6 +653,12 @@ struct ByteBuf {
     uint8_t operator[](size_t i) const { return p[i]; }
 };
 
+// A reference built with `--features blend` uses BlendCDF16 everywhere (src/interface.rs:146-147); a deployment that replaces such
+// a build says so once, through the environment of the process that loads this library: DIVANS_B200_FFI_CDF=blend.
+static bool ffi_cdf_blend() {
+    static const bool b = [] { const char *e = getenv("DIVANS_B200_FFI_CDF"); return e && strcmp(e, "blend") == 0; }();
+    return b;
+}
 struct DivansDecompressorState {
     HostAlloc al;
     bool self_in_custom = false;
@@ -754,7 +760,7 @@ extern "C" DivansResult divans_decode(DivansDecompressorState *s, const uint8_t 
             if (!s->outbuf.resize(cap)) { s->failed = true; return DIVANS_FAILURE; }
             uint64_t in_off = 0, in_len = s->inbuf.size(), out_off = 0, out_cap = cap, out_len = 0; int32_t status = DIVANS_FAILURE;
             DivansResult r = divans_b200_decode_batch_host(ctx, 1, s->inbuf.data(), &in_off, &in_len, s->outbuf.data(), &out_off, &out_cap,
-                                                           &out_len, &status, s->skip_crc ? DIVANS_B200_FLAG_SKIP_CRC : 0);
+                                                           &out_len, &status, (s->skip_crc ? DIVANS_B200_FLAG_SKIP_CRC : 0u) | (ffi_cdf_blend() ? DIVANS_B200_FLAG_CDF_BLEND : 0u));
             if (r != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
             if (status == DIVANS_NEEDS_MORE_OUTPUT && cap < max_out) { s->outbuf.release(); cap *= 4; continue; }
             if (status != DIVANS_SUCCESS) { s->failed = true; return DIVANS_FAILURE; }
@@ -792,6 +798,7 @@ extern "C" DivansCompressorState *divans_new_compressor_with_custom_alloc(CAlloc
     s->al.a = a;
     divans_b200_encode_options_default(&s->opts);
     s->opts.dynamic_context_mixing = 1;   // DivansCompressorOptions::default(), src/interface.rs:462-484
+    s->opts.cdf_model = ffi_cdf_blend() ? DIVANS_B200_CDF_BLEND : DIVANS_B200_CDF_FREQUENTIST;
     s->inbuf.al = &s->al; s->outbuf.al = &s->al;
     return s;
 }

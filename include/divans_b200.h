@@ -114,7 +114,9 @@ typedef struct divans_b200_ctx divans_b200_ctx;
  * feature="blend", which swaps in BlendCDF16 for the whole crate (src/interface.rs:146-147, probability/blend_cdf.rs:109-208:
  * a division-free model that averages towards the coded symbol with a decaying rate and ignores the speeds).  Nothing in a
  * stream says which model coded it: the two sides have to agree, as with the reference's compile-time switch.  Blend streams
- * run on the generic per-nibble path (16 lanes per stream), not on the literal fast loops. */
+ * run on the generic per-nibble path (16 lanes per stream), not on the literal fast loops.  The reference's own entry points
+ * (section 1) have no argument for it: a process that stands in for a `--features blend` build sets DIVANS_B200_FFI_CDF=blend
+ * in its environment before the first divans_* call. */
 #define DIVANS_B200_CDF_FREQUENTIST 0
 #define DIVANS_B200_CDF_BLEND 1
 #define DIVANS_B200_FLAG_CDF_BLEND 8u

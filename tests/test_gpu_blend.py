@@ -110,3 +110,58 @@ def test_full_batch_round_trip(engine):
     streams = engine.encode(raws, divans_b200.encode_options(cdf_model=divans_b200.CDF_BLEND))
     res = engine.decode(streams, [len(r) + 64 for r in raws], divans_b200.FLAG_CDF_BLEND)
     assert all(st == 0 and out == r for (st, out), r in zip(res, raws))
+
+
+def test_reference_ffi_as_a_blend_deployment(oracle_blend, text):
+    """The reference's FFI has no option for the probability model (it is a cargo feature): a process that replaces a
+    `--features blend` build says so through DIVANS_B200_FFI_CDF=blend.  Run in a child process (the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    raw = text[:50000]
+    enc = oracle_blend.encode_raw(raw, oracle_blend.options(dynamic_context_mixing=1))
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "in.divans"), "wb").write(enc)
+        open(os.path.join(d, "in.raw"), "wb").write(raw)
+        code = (
+            "import io, sys\n"
+            "sys.path.insert(0, %r)\n"
+            "import divans_b200\n"
+            "enc = open(%r, 'rb').read(); raw = open(%r, 'rb').read()\n"
+            "rd = divans_b200.DivansDecompressorReader(io.BytesIO(enc), 4096)\n"
+            "out = bytearray(); chunk = bytearray(4096)\n"
+            "while True:\n"
+            "    n = rd.readinto(chunk)\n"
+            "    if not n: break\n"
+            "    out += chunk[:n]\n"
+            "rd.close()\n"
+            "assert bytes(out) == raw, 'FFI decode of a blend stream'\n"
+            "sink = io.BytesIO(); w = divans_b200.DivansCompressorWriter(sink); w.write(raw); w.close()\n"
+            "open(%r, 'wb').write(sink.getvalue())\n"
+        ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(d, "in.divans"), os.path.join(d, "in.raw"), os.path.join(d, "out.divans"))
+        env = dict(os.environ, DIVANS_B200_FFI_CDF="blend")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        mine = open(os.path.join(d, "out.divans"), "rb").read()
+    rc, back = oracle_blend.decode(mine)      # what the FFI compressor wrote is a blend stream the blend oracle reads
+    assert rc == 0 and back == raw
+
+
+def test_truncated_and_corrupt_blend_streams_match_the_oracle(engine, oracle_blend, text):
+    import divans_b200
+    raw = text[:20000]
+    enc = oracle_blend.encode_raw(raw)
+    rng = np.random.default_rng(17)
+    streams = [enc[:k] for k in (0, 7, 16, 40, len(enc) // 2, len(enc) - 9, len(enc) - 1)]
+    for _ in range(24):
+        b = bytearray(enc)
+        pos = int(rng.integers(16, len(enc) - 8))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        streams.append(bytes(b))
+    caps = [len(raw) + 64] * len(streams)
+    res = engine.decode(streams, caps, divans_b200.FLAG_CDF_BLEND | divans_b200.FLAG_SKIP_CRC)
+    for i, (st, out) in enumerate(res):
+        rc, ref = oracle_blend.decode(streams[i], out_cap=caps[i], skip_crc=True)
+        assert st == rc, (i, st, rc)
+        if rc == 0:
+            assert out == ref, i
