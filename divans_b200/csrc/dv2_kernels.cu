@@ -30,7 +30,12 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
     g.blend = false;
 
     St s;
-    s.slot = p.arena + (uint64_t)slot * SLOT_STRIDE;
+    {   // (kept opaque: the compiler would rather rebuild this pointer from blockIdx and the parameter block at the head of
+        // every iteration -- seven instructions -- than hold it)
+        unsigned long long sp = reinterpret_cast<unsigned long long>(p.arena + (uint64_t)slot * SLOT_STRIDE);
+        asm volatile("" : "+l"(sp));
+        s.slot = reinterpret_cast<uint8_t *>(sp);
+    }
     s.c = reinterpret_cast<Cold *>(smem + group_in_block * SMEM_BYTES_PER_GROUP_V2);
     s.tables = p.tables;
     s.state = S_IDLE;
@@ -45,18 +50,18 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
     coder_init_dec(s.cur, nullptr, 0); s.cur.need_a = 0; coder_init_dec(s.c->oth, nullptr, 0);
     Next nx; nx.cdf = A_misc(s, MI_DUMMY); nx.cdf2 = nullptr; nx.speed = SPK_NONE; nx.sym = 0; nx.mix_hi = false; nx.tagged = false;
     store_default_cdfs(g, reinterpret_cast<int16_t *>(s.slot + OFF_MISC), (uint32_t)MISC_CDFS);   // incl. the dummy CDF
-    bool exhausted = false;
+    constexpr int S_DONE = -1;   // idle and the work queue is empty (v2 kernel only; one register less than a separate flag)
 
     for (;;) {
         __syncwarp();
         // ---- fetch work for idle groups (converged; the broadcast shuffle is executed by every lane) ----
-        const bool want = (s.state == S_IDLE) && !exhausted;
+        const bool want = s.state == S_IDLE;
         if (__any_sync(FULL, want)) {
             uint32_t v = 0;
             if (want && g.store0) v = atomicAdd(p.work_counter, 1u);
             v = __shfl_sync(FULL, v, 0, LPG);
             if (want) {
-                if (v >= p.n_streams) exhausted = true;
+                if (v >= p.n_streams) s.state = S_DONE;
                 else if (p.status[v] != ST_OK) { if (g.store0) p.out_len[v] = 0; }   // framing / CRC failure: stay idle, fetch again
                 else {
                     const uint8_t *in = p.in + p.in_off[v];
@@ -85,12 +90,12 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
                     enter_cmd_type<false>(s, nx);
                 }
             }
-            if (__all_sync(FULL, exhausted && s.state == S_IDLE)) break;
+            if (__all_sync(FULL, s.state == S_DONE)) break;
             __syncwarp();
         }
         // ---- whole literal bytes while every group is at a byte boundary of a literal (or out of work) ----
         const bool lit = s.state == S_LIT_HI;
-        if (__all_sync(FULL, lit || (exhausted && s.state == S_IDLE)) && __any_sync(FULL, lit) && literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy)) {
+        if (__any_sync(FULL, lit) && __all_sync(FULL, lit || s.state == S_DONE) && literal_fast_v2<LPG, PF>(s, nx, g, lit, smem_dummy)) {   // (the cheaper, usually false test first)
             if (lit) {
                 if (s.cur.underflow) s.status = ST_NEED_INPUT;
                 if (s.lit_left == 0 && s.status == ST_OK) { swap_coders(s, g); enter_cmd_type<false>(s, nx); }
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(DEC2_BLOCK_THREADS, DEC2_MIN_BLOCKS) decode_ke
             continue;
         }
         // ---- one nibble per group ----
-        const bool busy = s.state != S_IDLE;
+        const bool busy = s.state > S_IDLE;
         const int sym = nibble_core_v2<LPG>(s, nx, g);
         // ---- per-group scalar state machines (divergent) ----
         if (busy) {

@@ -300,6 +300,46 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         if (--s.lit_left != 0) { lit_context(s); enter_lit_nibble<ENC, true, V2>(s, nx); return; }
         swap_coders(s, g);
         tail = 1;
+    } else if (s.state >= S_CP_MNEMONIC && s.state <= S_CP_DIST_MANT) {
+        // ---- copy distance (codec/copy.rs:166-280): half of the command nibbles of a copy-dominated stream, tested before the switch
+        uint32_t dist = 0; bool done = false;
+        if (s.state == S_CP_DIST_MANT) {
+            uint32_t next_rem = s.f1 - 4;
+            s.f2 |= (uint32_t)nib << next_rem;
+            s.lit_h += 4;
+            if (next_rem == 0) { dist = s.f2; done = true; }
+            else { s.f1 = next_rem; enter_cp_dist_mant<ENC>(s, nx, g); }
+        } else if (s.state == S_CP_MNEMONIC) {
+            if (nib != 15) {
+                bool ok; distance_from_mnemonic(s, (uint32_t)nib, dist, ok);
+                s.c->last_dlen = bitlen32(dist);
+                if (!ok) { s.status = ST_FAIL; return; }   // CopyDistanceMnemonicCodeBad
+                done = true;
+            } else {
+                s.state = S_CP_DIST_BEG;
+                uint32_t dlen = bitlen32(s.c->e0);
+                int sym = (int)min(14u, (dlen - 1u) & 0xffu);
+                if (ENC && (s.c->lru1 - 3u) == s.c->e0 && !s.c->model_rev) sym = 15;   // copy.rs:199-201 (the model_rev 1 encoder did not take the shortcut)
+                set_next<ENC>(nx, dprior_slab(s, g, s.f3) + (DP_DIST_BEG + (bitlen32(s.f0) >> 2)) * 16, SPK_SLOW, sym);
+            }
+        } else if (s.state == S_CP_DIST_BEG) {
+            if (nib == 15) { dist = s.c->lru1 - 3u; s.c->last_dlen = bitlen32(dist); done = true; }
+            else if (nib == 0) { s.c->last_dlen = 1; dist = 1; done = true; }
+            else if (nib == 14) { s.state = S_CP_DIST_LAST; set_next<ENC>(nx, dprior_slab(s, g, s.f3) + DP_DIST_LAST * 16, SPK_ROCKET, (int)((bitlen32(s.c->e0) - 15u) & 0xf)); }
+            else { s.c->last_dlen = (uint32_t)nib + 1; s.f1 = round_up_mod_4((uint32_t)nib); s.f2 = 1u << nib; s.lit_h = 0; enter_cp_dist_mant<ENC>(s, nx, g); }
+        } else {   // S_CP_DIST_LAST
+            s.c->last_dlen = (uint32_t)nib + 15; s.f1 = round_up_mod_4((uint32_t)nib + 14); s.f2 = (nib + 14) < 32 ? (1u << (nib + 14)) : 0u; s.lit_h = 0;
+            enter_cp_dist_mant<ENC>(s, nx, g);
+        }
+        if (done) {
+            obs_distance(s, dist);
+            uint32_t len = s.f0;
+            if (dist == 0 || dist >= s.c->ring_len) { s.status = ST_FAIL; return; }   // DistanceGreaterRingBuffer & friends
+            if ((uint64_t)len > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
+            replay_copy(g, s.out, s.out_pos, dist, len);
+            s.out_pos += len;
+            tail = 1;
+        }
     } else
     switch (s.state) {
     case S_CMD_TYPE: {
@@ -375,46 +415,6 @@ __device__ __forceinline__ void transition(St &s, Next &nx, const G2 g, int nib)
         s.f0 |= (uint32_t)nib << next_rem;
         if (next_rem == 0) enter_cp_mnemonic<ENC>(s, nx, g);
         else { s.f1 = next_rem; s.f2 += 4; enter_cp_count_mant<ENC>(s, nx, g); }
-    } break;
-    case S_CP_MNEMONIC: case S_CP_DIST_BEG: case S_CP_DIST_LAST: case S_CP_DIST_MANT: {
-        uint32_t dist = 0; bool done = false;
-        if (s.state == S_CP_MNEMONIC) {
-            if (nib != 15) {
-                bool ok; distance_from_mnemonic(s, (uint32_t)nib, dist, ok);
-                s.c->last_dlen = bitlen32(dist);
-                if (!ok) { s.status = ST_FAIL; return; }   // CopyDistanceMnemonicCodeBad
-                done = true;
-            } else {
-                s.state = S_CP_DIST_BEG;
-                uint32_t dlen = bitlen32(s.c->e0);
-                int sym = (int)min(14u, (dlen - 1u) & 0xffu);
-                if (ENC && (s.c->lru1 - 3u) == s.c->e0 && !s.c->model_rev) sym = 15;   // copy.rs:199-201 (the model_rev 1 encoder did not take the shortcut)
-                set_next<ENC>(nx, dprior_slab(s, g, s.f3) + (DP_DIST_BEG + (bitlen32(s.f0) >> 2)) * 16, SPK_SLOW, sym);
-            }
-        } else if (s.state == S_CP_DIST_BEG) {
-            if (nib == 15) { dist = s.c->lru1 - 3u; s.c->last_dlen = bitlen32(dist); done = true; }
-            else if (nib == 0) { s.c->last_dlen = 1; dist = 1; done = true; }
-            else if (nib == 14) { s.state = S_CP_DIST_LAST; set_next<ENC>(nx, dprior_slab(s, g, s.f3) + DP_DIST_LAST * 16, SPK_ROCKET, (int)((bitlen32(s.c->e0) - 15u) & 0xf)); }
-            else { s.c->last_dlen = (uint32_t)nib + 1; s.f1 = round_up_mod_4((uint32_t)nib); s.f2 = 1u << nib; s.lit_h = 0; enter_cp_dist_mant<ENC>(s, nx, g); }
-        } else if (s.state == S_CP_DIST_LAST) {
-            s.c->last_dlen = (uint32_t)nib + 15; s.f1 = round_up_mod_4((uint32_t)nib + 14); s.f2 = (nib + 14) < 32 ? (1u << (nib + 14)) : 0u; s.lit_h = 0;
-            enter_cp_dist_mant<ENC>(s, nx, g);
-        } else {
-            uint32_t next_rem = s.f1 - 4;
-            s.f2 |= (uint32_t)nib << next_rem;
-            s.lit_h += 4;
-            if (next_rem == 0) { dist = s.f2; done = true; }
-            else { s.f1 = next_rem; enter_cp_dist_mant<ENC>(s, nx, g); }
-        }
-        if (done) {
-            obs_distance(s, dist);
-            uint32_t len = s.f0;
-            if (dist == 0 || dist >= s.c->ring_len) { s.status = ST_FAIL; return; }   // DistanceGreaterRingBuffer & friends
-            if ((uint64_t)len > (uint64_t)(s.c->out_cap - s.out_pos)) { s.status = ST_NEED_OUTPUT; return; }
-            replay_copy(g, s.out, s.out_pos, dist, len);
-            s.out_pos += len;
-            tail = 1;
-        }
     } break;
     // ---- dict ----
     case S_DC_SIZE_BEG: case S_DC_SIZE_LAST: {

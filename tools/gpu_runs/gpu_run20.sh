@@ -1,0 +1,14 @@
+#!/bin/bash
+# r2.9 (copy-distance states ahead of the switch, cheaper fast-path test) vs r2.8 on one box; tests; traffic captures + bench of the final library
+cd /root/repo; mkdir -p gpurun_out; T=r2_v17
+cp divans_b200/lib/libdivans_b200.so /tmp/new.so; cp divans_b200/lib/alt/libdivans_b200.so /tmp/alt.so
+for round in 1 2; do for V in new alt; do
+  cp /tmp/$V.so divans_b200/lib/libdivans_b200.so
+  echo "== $V (round $round)" | tee -a gpurun_out/${T}_ab.txt
+  timeout 300 python tools/zprobe.py 4096 2>&1 | tail -1 | tee -a gpurun_out/${T}_ab.txt
+  timeout 300 python tools/perf_probe.py --l-only --decode-once 4096 2>&1 | cut -c1-150 | tee -a gpurun_out/${T}_ab.txt
+done; done
+cp /tmp/new.so divans_b200/lib/libdivans_b200.so
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${T}_pytest.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel_v2 -c 1 -o gpurun_out/${T}_dec16_4096 python tools/perf_probe.py --l-only --decode-once 4096 > gpurun_out/${T}_ncu16.log 2>&1; echo "ncu16 rc=$?"
+DIVANS_B200_LPS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel_v2 -c 1 -o gpurun_out/${T}_dec8_8192 python tools/perf_probe.py --l-only --decode-once 8192 > gpurun_out/${T}_ncu8.log 2>&1; echo "ncu8 rc=$?"
