@@ -500,7 +500,10 @@ __device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, con
                 touch_l1(mk_ptr(lo_tab + row_l * 32u + (LPG == 16 ? li * 32u : li * 64u), slot_hi), smem_dummy);
                 if (LPG == 8) touch_l1(mk_ptr(lo_tab + row_l * 32u + li * 64u + 32u, slot_hi), smem_dummy);
             }
-#pragma unroll 2
+// (not unrolled: the literal loop itself times the same with 1, 2 or 4 bytes per trip -- 45.1-46.8 ms over two rounds each --
+            // but the command path, which is instruction-fetch bound, takes 119 ms with the smaller kernel instead of 129;
+            // profiles/r2_v18_variants.txt)
+#pragma unroll 1
             for (uint32_t i = 0; i < m; i++) {
                 // -- high nibble: search (speculative: the prior is almost always one this stream has written)
                 uint32_t eh_v = eh & ~tbits, mh_v = mh & 0x7fffu;
