@@ -500,10 +500,11 @@ __device__ __forceinline__ bool literal_fast_v2(St &s, Next &nx, const G2 g, con
                 touch_l1(mk_ptr(lo_tab + row_l * 32u + (LPG == 16 ? li * 32u : li * 64u), slot_hi), smem_dummy);
                 if (LPG == 8) touch_l1(mk_ptr(lo_tab + row_l * 32u + li * 64u + 32u, slot_hi), smem_dummy);
             }
-// (not unrolled: the literal loop itself times the same with 1, 2 or 4 bytes per trip -- 45.1-46.8 ms over two rounds each --
-            // but the command path, which is instruction-fetch bound, takes 119 ms with the smaller kernel instead of 129;
-            // profiles/r2_v18_variants.txt)
-#pragma unroll 1
+// (16 lanes per stream: not unrolled -- the literal loop itself times the same with 1, 2 or 4 bytes per trip, 45.1-46.8 ms over
+            // two rounds each, but the command path, which is instruction-fetch bound, takes 119 ms with the smaller kernel instead
+            // of 129, profiles/r2_v18_variants.txt.  8 lanes per stream: two bytes per trip, 73.4 vs 76.3 ms for 8192 streams,
+            // profiles/r2_v19_ab8.txt)
+#pragma unroll (LPG == 16 ? 1 : 2)
             for (uint32_t i = 0; i < m; i++) {
                 // -- high nibble: search (speculative: the prior is almost always one this stream has written)
                 uint32_t eh_v = eh & ~tbits, mh_v = mh & 0x7fffu;

@@ -179,7 +179,7 @@ extern "C" void divans_b200_destroy(divans_b200_ctx *ctx) {
     delete ctx;
 }
 // bumped whenever a decode kernel changes: profiles/traffic.json (an ncu capture) is only quoted by bench.py for the version it measured
-#define DV_KERNEL_VERSION "r2.10-v2-signtags"
+#define DV_KERNEL_VERSION "r2.11-v2-signtags"
 extern "C" const char *divans_b200_kernel_version(void) { return DV_KERNEL_VERSION; }
 extern "C" const char *divans_b200_last_error(divans_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int divans_b200_last_lanes(divans_b200_ctx *ctx) { return ctx ? ctx->last_lanes : 0; }
