@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <new>
 
 #include <algorithm>
 #include <mutex>
@@ -100,7 +101,8 @@ static bool grow(divans_b200_ctx *ctx, T **p, size_t *cap, size_t need) {
 }
 
 extern "C" divans_b200_ctx *divans_b200_create(int device, uint32_t max_resident, uint32_t lanes_per_stream) {
-    divans_b200_ctx *ctx = new divans_b200_ctx();
+    divans_b200_ctx *ctx = new (std::nothrow) divans_b200_ctx();
+    if (!ctx) return nullptr;
     ctx->device = device;
     // 16 (default, also 0): v2 engine, two streams per warp; 8: v2 engine, four streams per warp; 32: the round-1 kernel with one
     // warp per stream; 116: the round-1 16-lane kernel (kept for A/B measurements)
@@ -594,13 +596,16 @@ extern "C" DivansResult divans_b200_encode_batch_host(divans_b200_ctx *ctx, size
                                                       const uint64_t *in_len, uint8_t *out, const uint64_t *out_off,
                                                       const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
                                                       const divans_b200_encode_options *opts) {
-    return encode_host_common(ctx, n, 1, in, in_off, in_len, out, out_off, out_cap, out_len, status, opts);
+    // (host marshalling uses std::vector sized by the caller's arguments: no C++ exception may cross the C boundary)
+    try { return encode_host_common(ctx, n, 1, in, in_off, in_len, out, out_off, out_cap, out_len, status, opts); }
+    catch (...) { if (ctx) ctx->err = "divans_b200: out of host memory while marshalling the batch"; return DIVANS_FAILURE; }
 }
 extern "C" DivansResult divans_b200_encode_cmds_batch_host(divans_b200_ctx *ctx, size_t n, const uint8_t *blobs, const uint64_t *blob_off,
                                                            const uint64_t *blob_len, uint8_t *out, const uint64_t *out_off,
                                                            const uint64_t *out_cap, uint64_t *out_len, int32_t *status,
                                                            const divans_b200_encode_options *opts) {
-    return encode_host_common(ctx, n, 0, blobs, blob_off, blob_len, out, out_off, out_cap, out_len, status, opts);
+    try { return encode_host_common(ctx, n, 0, blobs, blob_off, blob_len, out, out_off, out_cap, out_len, status, opts); }
+    catch (...) { if (ctx) ctx->err = "divans_b200: out of host memory while marshalling the batch"; return DIVANS_FAILURE; }
 }
 
 // =================================================================================================================
@@ -677,7 +682,8 @@ static DivansDecompressorState *new_decomp(CAllocator a, uint8_t skip_crc) {
         if (!mem) return nullptr;
         s = new (mem) DivansDecompressorState();
         s->self_in_custom = true;
-    } else s = new DivansDecompressorState();
+    } else s = new (std::nothrow) DivansDecompressorState();
+    if (!s) return nullptr;
     s->al.a = a; s->skip_crc = skip_crc;
     s->inbuf.al = &s->al; s->outbuf.al = &s->al;
     if (!shared_ctx()) { s->failed = true; }
@@ -794,7 +800,8 @@ extern "C" DivansCompressorState *divans_new_compressor_with_custom_alloc(CAlloc
         void *mem = a.alloc_func(a.opaque, sizeof(DivansCompressorState));
         if (!mem) return nullptr;
         s = new (mem) DivansCompressorState(); s->self_in_custom = true;
-    } else s = new DivansCompressorState();
+    } else s = new (std::nothrow) DivansCompressorState();
+    if (!s) return nullptr;
     s->al.a = a;
     divans_b200_encode_options_default(&s->opts);
     s->opts.dynamic_context_mixing = 1;   // DivansCompressorOptions::default(), src/interface.rs:462-484
