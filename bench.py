@@ -596,8 +596,8 @@ def main():
                                                        "model_kernel_ms": enc2_model_ms, "compressed_bytes": enc2_bytes},
                           "default_options": {"value": out_bytes / (enc_ms / 1e3) / 1e6, "ms_per_step": enc_ms,
                                               "model_kernel_ms": enc_model_ms, "compressed_bytes": comp_bytes},
-                          "note": "rank 0's shard (BASELINE configs[3] shape: 4096 x 64 KiB), inputs and outputs resident in HBM; "
-                                  "literal-only command generator (the brotli quality-11 command selection is out of scope)"}
+                          "note": "rank 0's shard (%d x 64 KiB; BASELINE configs[3] is 4096 x 64 KiB), inputs and outputs resident in HBM; "
+                                  "literal-only command generator (the brotli quality-11 command selection is out of scope)" % n}
         if populations is not None:
             line["populations"] = populations
         if scattered is not None:
