@@ -195,3 +195,17 @@ def test_ir_front_end_matches_oracle_parser(oracle):
             divans_b200.ir_to_cmds(bad + "\n")
         with pytest.raises(ValueError):
             oracle.Commands.from_ir(bad + "\n")
+
+
+def test_traffic_capture_is_stamped_with_the_library_version():
+    """bench.py only reports roofline.traffic from an ncu capture of the kernel version it runs (profiles/traffic.json): the
+    committed captures must belong to the committed kernels, one per bench workload (16 lanes x 4096 streams, 8 x 8192)."""
+    import json
+    import re
+    src = open(os.path.join(ROOT, "divans_b200", "csrc", "dv_capi.cu")).read()
+    version = re.search(r'#define DV_KERNEL_VERSION "([^"]+)"', src).group(1)
+    entries = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["entries"]
+    assert {(e["lanes_per_stream"], e["streams"]) for e in entries} >= {(16, 4096), (8, 8192)}
+    for e in entries:
+        assert e["kernel_version"] == version, (e["lanes_per_stream"], e["kernel_version"], version)
+        assert e["decode_kernel_dram_bytes_per_launch"] == e["dram_read_bytes"] + e["dram_write_bytes"] > 0
